@@ -1,0 +1,229 @@
+// Persistent warp-specialised tcgen05 GEMM mainloop for sm_100a, shared by KA (similarity + row
+// arg-max epilogue) and the projection GEMMs of KD (fp16 store epilogue).
+//
+//   D[b][m, n] = sum_k A[b][m, k] * Bm[b][n, k]        fp16 operands (K-major), fp32 accumulators
+//
+// One CTA = 320 threads: warp 0 TMA producer (one lane), warp 1 TMEM allocator + MMA issuer (one lane),
+// warps 2..9 epilogue (TMEM lane quadrant = warp_id % 4; column half = (warp_id - 2) / 4).
+// Shared memory: STAGES x (A tile 128x64 + B tile BNx64) fp16, 128-byte swizzled by TMA, consumed in
+// place by tcgen05.mma through shared-memory descriptors.  TMEM: two accumulators of BN fp32 columns
+// (double buffered) so the epilogue of tile i overlaps the MMAs of tile i+1.
+// A work item is (m_tile, b, [nt0, nt1)); CTAs stride over work items (persistent grid = #SMs).
+//
+// Epilogue policy `Epi` (all members __device__, called by every epilogue thread):
+//   void begin(int m_tile, int b, int row_in_tile);                  // new work item
+//   void tile(uint32_t taddr, int col0, int ncols);                  // this warp's 128-lane x (BN/2)-col
+//                                                                    // slice of a finished accumulator:
+//                                                                    // taddr = TMEM address of (lane
+//                                                                    // quadrant, first column), col0 =
+//                                                                    // global n of that column
+//   void end(int m_tile, int b, int row_in_tile);                    // work item finished
+#pragma once
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace vtm {
+namespace gemm {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int UK = 16;
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = 64 + EPI_WARPS * 32;
+constexpr uint32_t A_BYTES = BM * BK * 2;
+
+template <int BN>
+struct Cfg {
+  static_assert(BN == 128 || BN == 256, "BN must be 128 or 256");
+  static constexpr uint32_t B_BYTES = BN * BK * 2;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BN == 256 ? 4 : 6;
+  static constexpr uint32_t TMEM_COLS = 2 * BN;
+  static constexpr size_t SMEM_BYTES = 1024 + static_cast<size_t>(STAGES) * STAGE_BYTES + 256;
+};
+
+struct Work {
+  int batches;          // B
+  int m_tiles, n_tiles;
+  int tiles_per_split, n_splits;
+  int k_chunks;
+  int total;
+  __host__ void plan(int M, int N, int K, int B, int BN, int sms, int target_items_per_sm, int min_tiles) {
+    batches = B;
+    m_tiles = (M + BM - 1) / BM;
+    n_tiles = (N + BN - 1) / BN;
+    k_chunks = (K + BK - 1) / BK;
+    const long long base = static_cast<long long>(m_tiles) * B;
+    int s = 1;
+    while (base * s < static_cast<long long>(target_items_per_sm) * sms && s * 2 <= n_tiles &&
+           n_tiles / (s * 2) >= min_tiles)
+      s *= 2;
+    tiles_per_split = (n_tiles + s - 1) / s;
+    n_splits = (n_tiles + tiles_per_split - 1) / tiles_per_split;
+    total = static_cast<int>(base * n_splits);
+  }
+  __device__ __forceinline__ void decode(int w, int* m_tile, int* b, int* nt0, int* nt1) const {
+    *m_tile = w % m_tiles;
+    const int rest = w / m_tiles;
+    *b = rest % batches;
+    const int sp = rest / batches;
+    *nt0 = sp * tiles_per_split;
+    const int e = *nt0 + tiles_per_split;
+    *nt1 = e < n_tiles ? e : n_tiles;
+  }
+};
+
+template <int BN, class Epi>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+            const Work wk, Epi epi) {
+  using C = Cfg<BN>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment: required by the 128-byte swizzle pattern shared by TMA and UMMA descriptors
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * C::STAGE_BYTES;
+  // 8-byte slots: full[STAGES] | empty[STAGES] | tmem_full[2] | tmem_empty[2] | tmem base pointer
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_addr, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < wk.total; w += gridDim.x) {
+        int m_tile, b, nt0, nt1;
+        wk.decode(w, &m_tile, &b, &nt0, &nt1);
+        for (int nt = nt0; nt < nt1; ++nt) {
+          for (int kc = 0; kc < wk.k_chunks; ++kc) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+            mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
+            tma_load_3d(sa, &tmap_a, full_bar(stage), kc * BK, m_tile * BM, b);
+            tma_load_3d(sa + A_BYTES, &tmap_b, full_bar(stage), kc * BK, nt * BN, b);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t tile_ctr = 0;
+      for (int w = blockIdx.x; w < wk.total; w += gridDim.x) {
+        int m_tile, b, nt0, nt1;
+        wk.decode(w, &m_tile, &b, &nt0, &nt1);
+        for (int nt = nt0; nt < nt1; ++nt, ++tile_ctr) {
+          const uint32_t as = tile_ctr & 1u;
+          const uint32_t aphase = (tile_ctr >> 1) & 1u;
+          mbar_wait(tempty_bar(as), aphase ^ 1u);  // epilogue has drained this accumulator
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + as * BN;
+          for (int kc = 0; kc < wk.k_chunks; ++kc) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+            const uint64_t adesc = umma_desc_sw128_kmajor(sa);
+            const uint64_t bdesc = umma_desc_sw128_kmajor(sa + A_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UK; ++k) {
+              // +32 bytes per K step inside the swizzle atom = +2 in the (address >> 4) field
+              umma_f16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kc | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs retire
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+          umma_commit(tfull_bar(as));  // accumulator complete
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int quad = warp & 3;            // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;     // which BN/2-column half of the tile
+    const int row_in_tile = quad * 32 + lane;
+    uint32_t tile_ctr = 0;
+    Epi e = epi;  // per-thread mutable copy of the policy (kernel parameters are read-only)
+    for (int w = blockIdx.x; w < wk.total; w += gridDim.x) {
+      int m_tile, b, nt0, nt1;
+      wk.decode(w, &m_tile, &b, &nt0, &nt1);
+      e.begin(m_tile, b, row_in_tile);
+      for (int nt = nt0; nt < nt1; ++nt, ++tile_ctr) {
+        const uint32_t as = tile_ctr & 1u;
+        const uint32_t aphase = (tile_ctr >> 1) & 1u;
+        mbar_wait(tfull_bar(as), aphase);
+        tc_fence_after();
+        const uint32_t taddr =
+            tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + half * (BN / 2);
+        e.tile(taddr, nt * BN + half * (BN / 2), BN / 2);
+        // every tcgen05.ld issued by tile() has been waited on (tcgen05.wait::ld) before it returns
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(as));
+      }
+      e.end(m_tile, b, row_in_tile);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <int BN, class Epi>
+inline int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Work& wk, const Epi& epi, int sms,
+                  cudaStream_t stream) {
+  using C = Cfg<BN>;
+  int rc = cuda_rc(cudaFuncSetAttribute(gemm_kernel<BN, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(C::SMEM_BYTES)));
+  if (rc) return rc;
+  const int grid = wk.total < sms ? wk.total : sms;
+  gemm_kernel<BN, Epi><<<grid, THREADS, C::SMEM_BYTES, stream>>>(ta, tb, wk, epi);
+  return launch_rc();
+}
+
+inline int device_sms(int* sms) {
+  int dev = 0;
+  int rc = cuda_rc(cudaGetDevice(&dev));
+  if (rc) return rc;
+  return cuda_rc(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev));
+}
+
+}  // namespace gemm
+}  // namespace vtm

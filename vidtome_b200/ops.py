@@ -1,0 +1,189 @@
+"""Thin torch-tensor wrappers over the C-ABI (one function per entry point of include/vidtome_b200.h).
+
+torch is used here only for device memory and streams.  Every function requires CUDA fp16 / int32
+tensors and raises on anything else — there is no CPU or eager-PyTorch implementation behind these.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import VtmSplit, check
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _require(t: torch.Tensor, dtype, name: str) -> None:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"vidtome_b200: `{name}` must be a CUDA tensor (this path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"vidtome_b200: `{name}` must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"vidtome_b200: `{name}` must be contiguous")
+
+
+def split_counts(split: VtmSplit) -> Tuple[int, int]:
+    ns, nd = C.c_int32(), C.c_int32()
+    check(_lib.load().vtm_split_counts(C.byref(split), C.byref(ns), C.byref(nd)), "vtm_split_counts")
+    return ns.value, nd.value
+
+
+def merge_count(num_src: int, ratio: float) -> int:
+    return int(_lib.load().vtm_merge_count(num_src, float(ratio)))
+
+
+def normalize_split(x: torch.Tensor, rowmap: Optional[torch.Tensor], split: VtmSplit):
+    """K0.  x [B, N0, C] fp16; rowmap [B'|1, N] int32 or None.  Returns (a [B,Ns,C], b [B,Nd,C])."""
+    _require(x, torch.float16, "x")
+    B, _, Cc = x.shape
+    ns, nd = split_counts(split)
+    a = torch.empty((B, ns, Cc), dtype=torch.float16, device=x.device)
+    b = torch.empty((B, nd, Cc), dtype=torch.float16, device=x.device)
+    map_bs = 0
+    if rowmap is not None:
+        _require(rowmap, torch.int32, "rowmap")
+        map_bs = 0 if rowmap.shape[0] == 1 else rowmap.shape[1]
+    check(_lib.load().vtm_normalize_split(x.data_ptr(), x.stride(0), _ptr(rowmap), map_bs, C.byref(split),
+                                          B, Cc, a.data_ptr(), b.data_ptr(), _stream()),
+          "vtm_normalize_split")
+    return a, b
+
+
+def sim_argmax(a: torch.Tensor, b: torch.Tensor, align_batch: bool, simt: bool = False) -> torch.Tensor:
+    """KA.  Returns the packed keys [B'|Ns] as an int64 tensor (bit pattern of the uint64 keys)."""
+    _require(a, torch.float16, "a")
+    _require(b, torch.float16, "b")
+    B, Ns, Cc = a.shape
+    Nd = b.shape[1]
+    keys = torch.empty((1 if align_batch else B, Ns), dtype=torch.int64, device=a.device)
+    fn = _lib.load().vtm_sim_argmax_simt if simt else _lib.load().vtm_sim_argmax
+    check(fn(a.data_ptr(), b.data_ptr(), B, Ns, Nd, Cc, int(bool(align_batch)), keys.data_ptr(), _stream()),
+          "vtm_sim_argmax")
+    return keys
+
+
+def topr_sort(keys: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """KB1.  keys [Bp, Ns] -> (edge [Bp, Ns] int32, rank [Bp, Ns] int32)."""
+    _require(keys, torch.int64, "keys")
+    Bp, Ns = keys.shape
+    lib = _lib.load()
+    ws_bytes = lib.vtm_topr_workspace_bytes(Bp, Ns)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=keys.device)
+    edge = torch.empty((Bp, Ns), dtype=torch.int32, device=keys.device)
+    rank = torch.empty((Bp, Ns), dtype=torch.int32, device=keys.device)
+    check(lib.vtm_topr_sort(keys.data_ptr(), Bp, Ns, edge.data_ptr(), rank.data_ptr(), ws.data_ptr(),
+                            ws_bytes, _stream()), "vtm_topr_sort")
+    return edge, rank
+
+
+def compose_maps(split: VtmSplit, r: int, keys: torch.Tensor, edge: torch.Tensor, rank: torch.Tensor,
+                 mu_in: Optional[torch.Tensor], pi_in: Optional[torch.Tensor], pi_offset: int, N0: int):
+    """KB2.  Returns (mu_out [Bp, Ns-r+Nd], pi_out [Bp, N0])."""
+    Bp, Ns = keys.shape
+    ns, nd = split_counts(split)
+    assert ns == Ns
+    mu_out = torch.empty((Bp, Ns - r + nd), dtype=torch.int32, device=keys.device)
+    pi_out = torch.empty((Bp, N0), dtype=torch.int32, device=keys.device)
+    if mu_in is not None:
+        _require(mu_in, torch.int32, "mu_in")
+    if pi_in is not None:
+        _require(pi_in, torch.int32, "pi_in")
+    check(_lib.load().vtm_compose_maps(C.byref(split), r, Ns, nd, Bp, keys.data_ptr(), edge.data_ptr(),
+                                       rank.data_ptr(), _ptr(mu_in), _ptr(pi_in), pi_offset, N0,
+                                       mu_out.data_ptr(), pi_out.data_ptr(), _stream()), "vtm_compose_maps")
+    return mu_out, pi_out
+
+
+def decode_match(keys: torch.Tensor, edge: torch.Tensor, Nd: int, r: int, want_node: bool = False):
+    """Expand KA/KB1 results to the reference's int64 index tensors: (unm_idx, src_idx, dst_idx[, node_max, node_idx])."""
+    Bp, Ns = keys.shape
+    dev = keys.device
+    unm = torch.empty((Bp, Ns - r, 1), dtype=torch.int64, device=dev)
+    src = torch.empty((Bp, r, 1), dtype=torch.int64, device=dev)
+    dst = torch.empty((Bp, r, 1), dtype=torch.int64, device=dev)
+    nmax = torch.empty((Bp, Ns), dtype=torch.float16, device=dev) if want_node else None
+    nidx = torch.empty((Bp, Ns), dtype=torch.int64, device=dev) if want_node else None
+    check(_lib.load().vtm_decode_match(keys.data_ptr(), edge.data_ptr(), Bp, Ns, Nd, r, unm.data_ptr(),
+                                       src.data_ptr(), dst.data_ptr(), _ptr(nmax), _ptr(nidx), _stream()),
+          "vtm_decode_match")
+    return (unm, src, dst, nmax, nidx) if want_node else (unm, src, dst)
+
+
+def gather_rows(x: torch.Tensor, row_map: Optional[torch.Tensor], L: Optional[int] = None,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """KC.  y[b, i] = x[b, map[b, i]].  x [B, N, C]; map [B'|1, L] int32."""
+    _require(x, torch.float16, "x")
+    B, _, Cc = x.shape
+    map_bs = 0
+    if row_map is not None:
+        _require(row_map, torch.int32, "map")
+        L = row_map.shape[1]
+        map_bs = 0 if row_map.shape[0] == 1 else L
+    if out is None:
+        out = torch.empty((B, L, Cc), dtype=torch.float16, device=x.device)
+    check(_lib.load().vtm_gather_rows(x.data_ptr(), x.stride(0), _ptr(row_map), map_bs, B, L, Cc,
+                                      out.data_ptr(), out.stride(0), _stream()), "vtm_gather_rows")
+    return out
+
+
+def unmerge_add(y: torch.Tensor, row_map: torch.Tensor, resid: Optional[torch.Tensor]) -> torch.Tensor:
+    """KE.  out[b, p] = y[b, map[b, p]] (+ resid[b, p]).  y [B, L, C]; map [B'|1, N] int32; resid [B, N, C]."""
+    _require(y, torch.float16, "y")
+    _require(row_map, torch.int32, "map")
+    B, _, Cc = y.shape
+    N = row_map.shape[1]
+    map_bs = 0 if row_map.shape[0] == 1 else N
+    if resid is not None:
+        _require(resid, torch.float16, "resid")
+    out = torch.empty((B, N, Cc), dtype=torch.float16, device=y.device)
+    check(_lib.load().vtm_unmerge_add(y.data_ptr(), y.stride(0), row_map.data_ptr(), map_bs, _ptr(resid),
+                                      B, N, Cc, out.data_ptr(), _stream()), "vtm_unmerge_add")
+    return out
+
+
+def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """D = A W^T (+ bias) on tcgen05.  a [M, K], w [N, K] fp16."""
+    _require(a, torch.float16, "a")
+    _require(w, torch.float16, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    d = torch.empty((M, N), dtype=torch.float16, device=a.device)
+    if bias is not None:
+        _require(bias, torch.float16, "bias")
+    check(_lib.load().vtm_linear_f16(a.data_ptr(), w.data_ptr(), _ptr(bias), M, N, K, d.data_ptr(), N, _stream()),
+          "vtm_linear_f16")
+    return d
+
+
+def attention(x: torch.Tensor, w_qkv: torch.Tensor, w_o: torch.Tensor, b_o: Optional[torch.Tensor], heads: int,
+              scale: float) -> torch.Tensor:
+    """KD.  x [B, L, C] fp16 -> [B, L, C]."""
+    _require(x, torch.float16, "x")
+    _require(w_qkv, torch.float16, "w_qkv")
+    _require(w_o, torch.float16, "w_o")
+    B, L, Cc = x.shape
+    lib = _lib.load()
+    ws_bytes = lib.vtm_attention_workspace_bytes(B, L, Cc, heads)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    y = torch.empty_like(x)
+    check(lib.vtm_attention(x.data_ptr(), w_qkv.data_ptr(), w_o.data_ptr(), _ptr(b_o), B, L, Cc, heads,
+                            float(scale), y.data_ptr(), ws.data_ptr(), ws_bytes, _stream()), "vtm_attention")
+    return y
+
+
+def keys_to_score_arg(keys: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Unpack KA keys on the device with torch integer ops (test / debugging helper)."""
+    o = (keys >> 32) & 0xFFFF
+    hb = torch.where((o & 0x8000) != 0, o & 0x7FFF, o ^ 0xFFFF)
+    score = torch.where(hb >= 0x8000, hb - 0x10000, hb).to(torch.int16).view(torch.float16)
+    arg = 0xFFFFFFFF - (keys & 0xFFFFFFFF)
+    return score, arg

@@ -1,0 +1,389 @@
+"""Patch layer — the drop-in boundary.  Same API as the reference's vidtome/patch.py:
+`apply_patch / remove_patch / update_patch / collect_from_patch`, the `_tome_info` dict, the
+`module.generator` / `module.global_tokens` attributes and the `ToMeBlock` class swap (patch.py:206-387).
+
+What differs from the reference is inside `compute_merge` and the self-attention section of
+`ToMeBlock.forward` (patch.py:14-91, :139-169):
+  * every matching level runs as CUDA kernels through the C-ABI (merge.match_level);
+  * the per-level merge/unmerge closures are never chained: their int32 index maps are composed on the
+    device (KB2), so the merged tokens are produced by ONE row gather of the block input (KC) and the
+    unmerge + split_frame + residual add is ONE gather-add pass (KE);
+  * `module.global_tokens` stays in HBM (the reference parks it on the CPU, patch.py:80,82).
+The RNG protocol is unchanged: one `torch.randint` per local level and one `torch.rand` per block when
+global tokens exist, drawn from `module.generator` on the generator's device (merge.py:56-57, patch.py:62).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Any, Callable, Dict, List, Optional, Tuple, Type
+
+import torch
+
+from . import merge, ops
+from ._lib import VtmSplit
+from .utils import (func_warper, init_generator, isinstance_str, join_frame, join_warper, split_frame,
+                    split_warper)
+
+
+@dataclass
+class MergePlan:
+    """Composed result of compute_merge for one block call."""
+    fsize: int
+    N0: int                               # F * T tokens per sample before merging
+    merged_tokens: torch.Tensor           # [B, L, C] fp16, input of attn1
+    pi: torch.Tensor                      # [B'|1, N0] int32: out[b, p] = y[b, pi[b, p]]
+    levels: List[merge.LevelMatch] = field(default_factory=list)
+    randf: List[int] = field(default_factory=list)
+    coin: Optional[float] = None
+
+    def unmerge(self, y: torch.Tensor, **kwarg) -> torch.Tensor:
+        """u_a of the reference (patch.py:85,168): all unmerges + split_frame, one gather pass."""
+        out = ops.unmerge_add(y.contiguous(), self.pi, None)
+        return split_frame(out, self.fsize)
+
+    def unmerge_add(self, y: torch.Tensor, hidden_states: torch.Tensor) -> torch.Tensor:
+        """patch.py:168-169 fused: u_a(attn_output) + hidden_states in one pass (KE)."""
+        resid = join_frame(hidden_states.contiguous(), self.fsize)
+        out = ops.unmerge_add(y.contiguous(), self.pi, resid)
+        return split_frame(out, self.fsize)
+
+
+def build_merge_plan(module: torch.nn.Module, x: torch.Tensor, tome_info: Dict[str, Any]) -> Optional[MergePlan]:
+    """The body of compute_merge (vidtome/patch.py:14-91).  Returns None when the block is not merged
+    (downsample > max_downsample, patch.py:27,86-88)."""
+    original_h, original_w = tome_info["size"]
+    original_tokens = original_h * original_w
+    downsample = int(math.ceil(math.sqrt(original_tokens // x.shape[1])))    # patch.py:15-17
+    args = tome_info["args"]
+    if downsample > args["max_downsample"]:
+        return None
+    merge._check_metric(x)
+    generator = module.generator
+    fsize = x.shape[0] // args["batch_size"]                                 # patch.py:23
+    tsize = x.shape[1]                                                       # patch.py:24
+    align = bool(args["align_batch"])
+
+    table = join_frame(x.contiguous(), fsize)                                # patch.py:37 (view)
+    B, N0, C = table.shape
+    mu: Optional[torch.Tensor] = None      # position -> row of `table` (None = identity)
+    pi: Optional[torch.Tensor] = None      # level-0 position -> current position (None = identity)
+    L, unm, curF = N0, 0, fsize
+    levels: List[merge.LevelMatch] = []
+    randfs: List[int] = []
+    ratio = args["local_merge_ratio"]
+    while curF > 1:                                                          # patch.py:44
+        if ratio <= 0:
+            unm += (L - unm) // curF                                         # merge.py:45-46 (no draw)
+        else:
+            stride = min(args["target_stride"], curF)                        # merge.py:55
+            randf = int(torch.randint(0, stride, torch.Size([1]), generator=generator,
+                                      device=generator.device).item())      # merge.py:56-57
+            randfs.append(randf)
+            split = VtmSplit.local(L, unm, curF, args["target_stride"], randf)
+            m = merge.match_level(table, mu, split, ratio, align)            # patch.py:45-46
+            mu, pi = ops.compose_maps(split, m.r, m.keys, m.edge, m.rank, mu, pi, 0, N0)
+            levels.append(m)
+            unm += m.unm_num                                                 # patch.py:47
+            L = mu.shape[1]                                                  # patch.py:50
+        curF = (L - unm) // tsize                                            # patch.py:54
+
+    if mu is None:   # nothing merged (single frame or ratio <= 0): identity maps
+        mu = torch.arange(N0, dtype=torch.int32, device=x.device)[None]
+        pi = mu
+    coin = None
+    if args["merge_global"]:                                                 # patch.py:59
+        local_tokens = ops.gather_rows(table, mu)                            # merged local tokens [B, L, C]
+        g = getattr(module, "global_tokens", None)
+        if g is not None:                                                    # patch.py:60
+            coin = float(torch.rand(1, generator=generator, device=generator.device).item())  # patch.py:62
+            g = g.to(local_tokens).contiguous()                              # patch.py:65,70
+            Lg = g.shape[1]
+            if coin > args["global_rand"]:
+                src_len, tokens, off = L, torch.cat([local_tokens, g], dim=1), 0          # patch.py:63-66
+            else:
+                src_len, tokens, off = Lg, torch.cat([g, local_tokens], dim=1), Lg        # patch.py:68-71
+            gratio = args["global_merge_ratio"]
+            if gratio <= 0:
+                # merge.py:364-365 returns two values and patch.py:73 unpacks three
+                raise ValueError("not enough values to unpack (expected 3, got 2)")
+            split = VtmSplit.prefix(L + Lg, src_len)
+            m = merge.match_level(tokens, None, split, gratio, align)        # patch.py:73-74
+            levels.append(m)
+            # tau: position in `tokens` -> position in the merged sequence (the 2s unmerge as a map)
+            mu_g, tau = ops.compose_maps(split, m.r, m.keys, m.edge, m.rank, None, None, 0, L + Lg)
+            merged_tokens = ops.gather_rows(tokens, mu_g)                    # patch.py:75
+            # patch.py:80: global_tokens <- u(merged_tokens), the local partition after unmerging;
+            # kept on the device instead of .cpu()
+            tau_local = tau[:, off:off + L].contiguous()
+            module.global_tokens = ops.unmerge_add(merged_tokens, tau_local, None)
+            # compose with the local unmerge: pi_total[p] = tau[off + pi[p]]
+            if pi.shape[0] != tau.shape[0]:
+                pi = pi.expand(tau.shape[0], -1)
+            pi = torch.gather(tau, 1, (pi.long() + off)).to(torch.int32).contiguous()
+        else:
+            merged_tokens = local_tokens
+            module.global_tokens = local_tokens.detach().clone()            # patch.py:82
+    else:
+        merged_tokens = ops.gather_rows(table, mu)                           # patch.py:50,56 composed
+    return MergePlan(fsize=fsize, N0=N0, merged_tokens=merged_tokens, pi=pi, levels=levels, randf=randfs,
+                     coin=coin)
+
+
+def compute_merge(module: torch.nn.Module, x: torch.Tensor, tome_info: Dict[str, Any]) -> Tuple[Callable, ...]:
+    """Reference signature and return triple (patch.py:14,91): (merge op, unmerge op, merged tokens).
+    The merge op is returned for interface parity only — like the reference's diffusers block
+    (patch.py:149-152) nothing here calls it: the merged tokens are already the third element."""
+    plan = build_merge_plan(module, x, tome_info)
+    if plan is None:
+        return merge.do_nothing, merge.do_nothing, x                         # patch.py:86-88
+    merged = plan.merged_tokens
+
+    def m(_x: torch.Tensor, **kwarg) -> torch.Tensor:
+        return merged
+    u = plan.unmerge
+    u.plan = plan
+    return m, u, merged
+
+
+def _plain_attention_module(attn: torch.nn.Module) -> bool:
+    """True if `attn` is a stock diffusers-style Attention whose forward we may replace with KD:
+    to_q/to_k/to_v without bias, to_out = [Linear, Dropout], and no instance-level forward override
+    (PnP installs one, utils/pnp_utils.py:99-101)."""
+    if "forward" in vars(attn):
+        return False
+    need = ("to_q", "to_k", "to_v", "to_out", "heads")
+    if not all(hasattr(attn, n) for n in need):
+        return False
+    if any(getattr(attn, n).bias is not None for n in ("to_q", "to_k", "to_v")):
+        return False
+    to_out = attn.to_out
+    return isinstance(to_out, (torch.nn.ModuleList, torch.nn.Sequential)) and isinstance(to_out[0], torch.nn.Linear)
+
+
+def make_tome_block(block_class: Type[torch.nn.Module]) -> Type[torch.nn.Module]:
+    """CompVis-LDM variant (patch.py:94-116).  The reference's version unpacks six values from
+    compute_merge's three (patch.py:105 vs :91) and cannot run; we refuse at patch time instead."""
+    raise NotImplementedError(
+        "vidtome_b200: the LDM (non-diffusers) ToMeBlock of the reference is not runnable upstream "
+        "(patch.py:105 unpacks 6 values from a 3-tuple); only diffusers models are supported")
+
+
+def make_diffusers_tome_block(block_class: Type[torch.nn.Module]) -> Type[torch.nn.Module]:
+    """Patched class for a diffusers BasicTransformerBlock (patch.py:119-203)."""
+
+    class ToMeBlock(block_class):
+        # Save for unpatching later
+        _parent = block_class
+
+        def forward(self, hidden_states, attention_mask=None, encoder_hidden_states=None,
+                    encoder_attention_mask=None, timestep=None, cross_attention_kwargs=None,
+                    class_labels=None) -> torch.Tensor:
+            if self.use_ada_layer_norm:                                       # patch.py:139-146
+                norm_hidden_states = self.norm1(hidden_states, timestep)
+            elif self.use_ada_layer_norm_zero:
+                norm_hidden_states, gate_msa, shift_mlp, scale_mlp, gate_mlp = self.norm1(
+                    hidden_states, timestep, class_labels, hidden_dtype=hidden_states.dtype)
+            else:
+                norm_hidden_states = self.norm1(hidden_states)
+
+            plan = build_merge_plan(self, norm_hidden_states, self._tome_info)  # patch.py:149-150
+            if plan is not None:
+                norm_hidden_states = plan.merged_tokens
+
+            # 1. Self-Attention (patch.py:154-162)
+            cross_attention_kwargs = cross_attention_kwargs if cross_attention_kwargs is not None else {}
+            only_cross = getattr(self, "only_cross_attention", False)
+            from . import attention as _attention
+            if (plan is not None and _attention.ENABLED and not only_cross and attention_mask is None
+                    and not cross_attention_kwargs and _plain_attention_module(self.attn1)):
+                attn_output = _attention.self_attention(self.attn1, norm_hidden_states)  # KD
+            else:
+                attn_output = self.attn1(
+                    norm_hidden_states,
+                    encoder_hidden_states=encoder_hidden_states if only_cross else None,
+                    attention_mask=attention_mask, **cross_attention_kwargs)
+            if self.use_ada_layer_norm_zero:
+                attn_output = gate_msa.unsqueeze(1) * attn_output            # patch.py:164-165
+
+            # Unmerge + residual (patch.py:168-169), fused into one pass
+            if plan is not None:
+                hidden_states = plan.unmerge_add(attn_output, hidden_states)
+            else:
+                hidden_states = attn_output + hidden_states
+
+            if getattr(self, "attn2", None) is not None:                     # patch.py:171-185
+                norm_hidden_states = (self.norm2(hidden_states, timestep) if self.use_ada_layer_norm
+                                      else self.norm2(hidden_states))
+                attn_output = self.attn2(norm_hidden_states, encoder_hidden_states=encoder_hidden_states,
+                                         attention_mask=encoder_attention_mask, **cross_attention_kwargs)
+                hidden_states = attn_output + hidden_states
+
+            # 3. Feed-forward (patch.py:187-199).  A block without `ff` (the hot-path skeleton used by
+            # bench.py) stops after the self-attention section.
+            if getattr(self, "ff", None) is not None:
+                norm_hidden_states = self.norm3(hidden_states)
+                if self.use_ada_layer_norm_zero:
+                    norm_hidden_states = norm_hidden_states * (1 + scale_mlp[:, None]) + shift_mlp[:, None]
+                ff_output = self.ff(norm_hidden_states)
+                if self.use_ada_layer_norm_zero:
+                    ff_output = gate_mlp.unsqueeze(1) * ff_output
+                hidden_states = ff_output + hidden_states
+            return hidden_states
+
+    return ToMeBlock
+
+
+def hook_tome_model(model: torch.nn.Module):
+    """Forward pre-hook recording the latent size (patch.py:206-212).  The UNet must be called with the
+    latent as positional argument 0, as generate.py:275 does."""
+    def hook(module, args):
+        module._tome_info["size"] = (args[0].shape[2], args[0].shape[3])
+        return None
+
+    model._tome_info["hooks"].append(model.register_forward_pre_hook(hook))
+
+
+def hook_tome_module(module: torch.nn.Module):
+    """Forward pre-hook that forks the default RNG into `module.generator` on first use, so that all
+    blocks draw the same random target frames within one pass (patch.py:215-231)."""
+    def hook(module, args):
+        if not hasattr(module, "generator"):
+            module.generator = init_generator(args[0].device)
+        elif module.generator.device != args[0].device:
+            module.generator = init_generator(args[0].device, fallback=module.generator)
+        else:
+            return None
+        return None
+
+    module._tome_info["hooks"].append(module.register_forward_pre_hook(hook))
+
+
+def apply_patch(
+        model: torch.nn.Module,
+        local_merge_ratio: float = 0.9,
+        merge_global: bool = False,
+        global_merge_ratio=0.8,
+        max_downsample: int = 2,
+        seed: int = 123,
+        batch_size: int = 2,
+        include_control: bool = False,
+        align_batch: bool = False,
+        target_stride: int = 4,
+        global_rand=0.5):
+    """Patch a Stable-Diffusion model with VidToMe (signature, defaults and semantics of
+    vidtome/patch.py:234-334).
+
+     - model: a diffusers pipeline (uses `.unet`, and `.controlnet` when it is a
+       StableDiffusionControlNetPipeline and include_control) or a bare diffusers UNet; detected by class
+       NAME (DiffusionPipeline / ModelMixin), blocks by the name BasicTransformerBlock.
+     - local_merge_ratio: fraction of src tokens merged inside a frame chunk (0.9 -> 1.3/4.0 kept for 4 frames).
+     - merge_global / global_merge_ratio / global_rand: inter-chunk (global) token merging.
+     - max_downsample: merge only in layers with at most this downsampling (1, 2, 4 or 8).
+     - seed: stored, unused (as in the reference).   - batch_size: number of video chunks per pass (2 = CFG, 3 = PnP).
+     - align_batch: share one matching across the batch (PnP).   - target_stride: one target frame per this many frames.
+    """
+    # Make sure the module is not currently patched
+    remove_patch(model)
+
+    is_diffusers = isinstance_str(model, "DiffusionPipeline") or isinstance_str(model, "ModelMixin")
+
+    if not is_diffusers:
+        if not hasattr(model, "model") or not hasattr(model.model, "diffusion_model"):
+            # Provided model not supported
+            raise RuntimeError("Provided model was not a Stable Diffusion / Latent Diffusion model, as expected.")
+        diffusion_model = model.model.diffusion_model
+    else:
+        # Supports "pipe.unet" and "unet"
+        diffusion_model = model.unet if hasattr(model, "unet") else model
+
+    if isinstance_str(model, "StableDiffusionControlNetPipeline") and include_control:
+        diffusion_models = [diffusion_model, model.controlnet]
+    else:
+        diffusion_models = [diffusion_model]
+
+    from . import _lib
+    _lib.load()   # fail at patch time, loudly, if the CUDA library is missing
+
+    for diffusion_model in diffusion_models:
+        diffusion_model._tome_info = {
+            "size": None,
+            "hooks": [],
+            "args": {
+                "max_downsample": max_downsample,
+                "generator": None,
+                "seed": seed,
+                "batch_size": batch_size,
+                "align_batch": align_batch,
+                "merge_global": merge_global,
+                "global_merge_ratio": global_merge_ratio,
+                "local_merge_ratio": local_merge_ratio,
+                "global_rand": global_rand,
+                "target_stride": target_stride
+            }
+        }
+        hook_tome_model(diffusion_model)
+
+        for name, module in diffusion_model.named_modules():
+            if isinstance_str(module, "BasicTransformerBlock"):
+                make_tome_block_fn = make_diffusers_tome_block if is_diffusers else make_tome_block
+                module.__class__ = make_tome_block_fn(module.__class__)
+                module._tome_info = diffusion_model._tome_info
+                hook_tome_module(module)
+
+                # Something needed for older versions of diffusers
+                if not hasattr(module, "use_ada_layer_norm_zero") and is_diffusers:
+                    module.use_ada_layer_norm = False
+                    module.use_ada_layer_norm_zero = False
+
+    return model
+
+
+def _patched_roots(model: torch.nn.Module) -> List[torch.nn.Module]:
+    """The modules the un/update/collect calls walk: `model.unet` (or `model`) and, when that UNet object
+    itself carries one, its `.controlnet`.  (The reference looks for `.controlnet` on the UNet rather than
+    on the pipeline, patch.py:341-344,361-364,376-378, so a ControlNet patched through
+    include_control is not reached by these three calls; kept for drop-in behaviour.)"""
+    root = model.unet if hasattr(model, "unet") else model
+    roots = [root]
+    if hasattr(root, "controlnet"):
+        roots.append(root.controlnet)
+    return roots
+
+
+def remove_patch(model: torch.nn.Module):
+    """Undo apply_patch if the model is patched: drop the hooks and restore the block classes
+    (patch.py:337-355).  Returns the UNet (or the model itself), like the reference."""
+    roots = _patched_roots(model)
+    for root in roots:
+        for _, module in root.named_modules():
+            info = getattr(module, "_tome_info", None)
+            if info is not None:
+                for handle in info["hooks"]:
+                    handle.remove()
+                info["hooks"].clear()
+            if module.__class__.__name__ == "ToMeBlock":
+                module.__class__ = module._parent
+    return roots[-1]
+
+
+def update_patch(model: torch.nn.Module, **kwargs):
+    """Set attributes on every module that carries `_tome_info` (the UNet and each patched block), e.g.
+    `update_patch(pipe, global_tokens=None)` after each denoising step (patch.py:358-370,
+    generate.py:233-236)."""
+    for root in _patched_roots(model):
+        for _, module in root.named_modules():
+            if hasattr(module, "_tome_info"):
+                for key, value in kwargs.items():
+                    setattr(module, key, value)
+    return model
+
+
+def collect_from_patch(model: torch.nn.Module, attr="tome"):
+    """{qualified module name: getattr(module, attr)} for every module that has `attr` (patch.py:373-387)."""
+    found = dict()
+    for root in _patched_roots(model):
+        for name, module in root.named_modules():
+            if hasattr(module, attr):
+                found[name] = getattr(module, attr)
+    return found

@@ -1,0 +1,54 @@
+"""Token / RNG helpers with the reference's names and semantics (vidtome/utils.py:4-60)."""
+from __future__ import annotations
+
+import torch
+
+
+def isinstance_str(x: object, cls_name: str) -> bool:
+    """True if any class *named* cls_name is in x's MRO (vidtome/utils.py:4-16).  The patch API matches
+    diffusers classes by name so that it never has to import diffusers."""
+    return any(c.__name__ == cls_name for c in x.__class__.__mro__)
+
+
+def init_generator(device: torch.device, fallback: torch.Generator = None) -> torch.Generator:
+    """Fork the current default RNG state of `device` into a new generator (vidtome/utils.py:18-30)."""
+    if device.type == "cpu":
+        return torch.Generator(device="cpu").set_state(torch.get_rng_state())
+    if device.type == "cuda":
+        return torch.Generator(device=device).set_state(torch.cuda.get_rng_state())
+    if fallback is None:
+        return init_generator(torch.device("cpu"))
+    return fallback
+
+
+def join_frame(x: torch.Tensor, fsize: int) -> torch.Tensor:
+    """"(B F) N C -> B (F N) C" (vidtome/utils.py:32-35).  A view for contiguous input."""
+    bf, n, c = x.shape
+    return x.reshape(bf // fsize, fsize * n, c)
+
+
+def split_frame(x: torch.Tensor, fsize: int) -> torch.Tensor:
+    """"B (F N) C -> (B F) N C" (vidtome/utils.py:37-40)."""
+    b, fn, c = x.shape
+    return x.reshape(b * fsize, fn // fsize, c)
+
+
+def func_warper(funcs):
+    """Compose a list of ops left to right, passing keyword arguments through (vidtome/utils.py:42-48)."""
+    def fn(x, **kwarg):
+        for func in funcs:
+            x = func(x, **kwarg)
+        return x
+    return fn
+
+
+def join_warper(fsize):
+    def fn(x):
+        return join_frame(x, fsize)
+    return fn
+
+
+def split_warper(fsize):
+    def fn(x):
+        return split_frame(x, fsize)
+    return fn
