@@ -1,0 +1,195 @@
+"""CPU-only tests: the C-ABI library loads and exports every declared symbol, the pure-host entry points
+agree with the oracle, the patch API behaves like the reference's (class swap, hooks, attribute
+broadcast, error conventions), and the product refuses to run without CUDA (no fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import vidtome_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _lib():
+    from vidtome_b200 import _lib
+    return _lib.load()
+
+
+def test_library_exports_every_symbol_declared_in_header():
+    header = open(os.path.join(ROOT, "include", "vidtome_b200.h")).read()
+    declared = set(re.findall(r"\b(vtm_[a-z0-9_]+)\s*\(", header))
+    declared.discard("vtm_key_score")  # mentioned in a comment only
+    from vidtome_b200 import _lib
+    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _lib.load().vtm_version() == 100
+
+
+def test_library_has_no_driver_link_dependency():
+    """The library must load on a machine without libcuda (this container has none)."""
+    import subprocess
+    from vidtome_b200 import _lib
+    out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "libcuda.so" not in out and "libcudart" not in out
+
+
+def test_error_strings():
+    lib = _lib()
+    assert lib.vtm_error_string(0) == b"ok"
+    for code in (-1, -2, -3, -4, -5, -6):
+        assert len(lib.vtm_error_string(code)) > 3
+
+
+@pytest.mark.parametrize("N,unm_pre,F,stride", [(4 * 96, 0, 4, 4), (5 * 64 + 37, 37, 5, 4), (6 * 10, 0, 6, 4),
+                                               (2 * 50 + 11, 11, 2, 4), (3 * 7, 0, 3, 4), (16 * 8, 0, 16, 4)])
+def test_split_counts_match_oracle(N, unm_pre, F, stride):
+    from vidtome_b200 import ops
+    from vidtome_b200._lib import VtmSplit
+    for randf in range(min(stride, F)):
+        a_idx, b_idx, _, _ = O.split_indices_randframe(N, F, unm_pre, stride, randf)
+        assert ops.split_counts(VtmSplit.local(N, unm_pre, F, stride, randf)) == (len(a_idx), len(b_idx))
+    assert ops.split_counts(VtmSplit.prefix(100, 37)) == (37, 63)
+
+
+def test_split_rejects_inconsistent_descriptor():
+    from vidtome_b200._lib import VtmSplit
+    lib = _lib()
+    bad = VtmSplit(0, 100, 0, 3, 33, 3, 0, 0)          # 3 * 33 != 100
+    assert lib.vtm_split_counts(ctypes.byref(bad), None, None) == -3
+    bad = VtmSplit(0, 99, 0, 3, 33, 3, 3, 0)           # randf out of range
+    assert lib.vtm_split_counts(ctypes.byref(bad), None, None) == -3
+    bad = VtmSplit(1, 10, 0, 0, 0, 0, 0, 11)           # src_len > N
+    assert lib.vtm_split_counts(ctypes.byref(bad), None, None) == -3
+
+
+def test_merge_count_matches_python_truncation():
+    from vidtome_b200 import ops
+    rng = np.random.default_rng(0)
+    for ns in [0, 1, 7, 3072, 12288, 49152, 5325, 55296, 9216] + list(rng.integers(1, 100000, 50)):
+        for ratio in (0.9, 0.8, 0.95, 0.5, 1.0, 1.7, 0.3333333, 1e-9):
+            assert ops.merge_count(int(ns), ratio) == O.merge_count(int(ns), ratio)
+
+
+def test_compute_entry_points_validate_arguments_without_a_device():
+    lib = _lib()
+    assert lib.vtm_sim_argmax(None, None, 1, 1, 1, 8, 0, None, None) == -1
+    assert lib.vtm_sim_argmax(1, 1, 1, 16, 16, 12, 0, 1, None) == -2          # C % 8 != 0
+    assert lib.vtm_gather_rows(None, 0, None, 0, 1, 1, 8, None, 0, None) == -1
+    assert lib.vtm_topr_sort(1, 1, 16, 1, 1, 1, 0, None) == -4                # workspace too small
+    assert lib.vtm_linear_f16(1, 1, None, 16, 12, 64, 1, 12, None) == -2
+
+
+# --------------------------------------------------------------------------- patch API (no CUDA needed)
+def _skeleton():
+    from vidtome_b200.skeleton import make_skeleton
+    return make_skeleton("tiny", device="cpu", dtype=torch.float32)
+
+
+def test_package_exports_match_reference():
+    import vidtome_b200
+    assert vidtome_b200.__all__ == ["merge", "patch", "apply_patch", "remove_patch", "update_patch",
+                                    "collect_from_patch"]
+    import inspect
+    sig = inspect.signature(vidtome_b200.apply_patch)
+    assert list(sig.parameters) == ["model", "local_merge_ratio", "merge_global", "global_merge_ratio",
+                                    "max_downsample", "seed", "batch_size", "include_control", "align_batch",
+                                    "target_stride", "global_rand"]
+    d = {k: v.default for k, v in sig.parameters.items() if k != "model"}
+    assert d == dict(local_merge_ratio=0.9, merge_global=False, global_merge_ratio=0.8, max_downsample=2,
+                     seed=123, batch_size=2, include_control=False, align_batch=False, target_stride=4,
+                     global_rand=0.5)
+
+
+def test_apply_and_remove_patch_swap_classes_and_hooks():
+    import vidtome_b200
+    net = _skeleton()
+    out = vidtome_b200.apply_patch(net, local_merge_ratio=0.8, merge_global=True, batch_size=3)
+    assert out is net
+    blocks = [m for m in net.modules() if type(m).__name__ == "ToMeBlock"]
+    assert len(blocks) == 4
+    info = net._tome_info
+    assert info["size"] is None and len(info["hooks"]) == 1 + 4
+    assert info["args"] == dict(max_downsample=2, generator=None, seed=123, batch_size=3, align_batch=False,
+                                merge_global=True, global_merge_ratio=0.8, local_merge_ratio=0.8,
+                                global_rand=0.5, target_stride=4)
+    assert all(b._tome_info is info for b in blocks)
+    assert all(type(b)._parent.__name__ == "BasicTransformerBlock" for b in blocks)
+    # update_patch reaches the UNet and every block (patch.py:358-370)
+    vidtome_b200.update_patch(net, global_tokens=None, foo=3)
+    assert net.foo == 3 and all(b.foo == 3 and b.global_tokens is None for b in blocks)
+    got = vidtome_b200.collect_from_patch(net, attr="foo")
+    assert set(got.values()) == {3} and len(got) == 5 and "" in got
+    # re-applying first removes the old patch (patch.py:277)
+    vidtome_b200.apply_patch(net)
+    assert len(net._tome_info["hooks"]) == 5
+    vidtome_b200.remove_patch(net)
+    assert not [m for m in net.modules() if type(m).__name__ == "ToMeBlock"]
+    assert net._tome_info["hooks"] == []
+
+
+def test_apply_patch_rejects_unsupported_model():
+    import vidtome_b200
+    with pytest.raises(RuntimeError, match="not a Stable Diffusion"):
+        vidtome_b200.apply_patch(torch.nn.Linear(2, 2))
+
+
+def test_pipeline_like_object_with_unet_attribute():
+    import vidtome_b200
+
+    class DiffusionPipeline:           # matched by NAME (patch.py:279)
+        def __init__(self, unet):
+            self.unet = unet
+
+    pipe = DiffusionPipeline(_skeleton())
+    vidtome_b200.apply_patch(pipe)
+    assert hasattr(pipe.unet, "_tome_info")
+    assert vidtome_b200.remove_patch(pipe) is pipe.unet
+
+
+def test_no_cpu_fallback():
+    """CPU tensors must be refused loudly — never computed some other way."""
+    import vidtome_b200
+    from vidtome_b200 import merge
+    x = torch.randn(2, 64, 16)
+    g = torch.Generator().manual_seed(0)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        merge.bipartite_soft_matching_randframe(x.half(), 4, 0.9, 0, g)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        merge.bipartite_soft_matching_2s(x.half(), 32, 0.8, False)
+    net = _skeleton()
+    vidtome_b200.apply_patch(net)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        net(torch.randn(8, 4, 8, 8), 0)
+    # ratio <= 0 keeps the reference's identity behaviour and arity (merge.py:45-46, :364-365)
+    m, u, ret = merge.bipartite_soft_matching_randframe(x, 4, 0.0, 0, g)
+    assert m(x) is x and ret == {"unm_num": 16}
+    assert len(merge.bipartite_soft_matching_2s(x, 32, 0.0, False)) == 2
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "vidtome_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "vidtome_oracle" not in src and "import oracle" not in src, f
+
+
+def test_generators_stay_in_lockstep_hooks():
+    """hook_tome_module forks the default RNG state into module.generator on first forward
+    (patch.py:215-231); all blocks get the same state."""
+    import vidtome_b200
+    from vidtome_b200 import patch
+    net = _skeleton()
+    vidtome_b200.apply_patch(net, max_downsample=0)    # nothing merges -> runs on CPU through plain attention
+    torch.manual_seed(5)
+    net(torch.randn(8, 4, 8, 8), 0)
+    states = [b.generator.get_state() for b in net.blocks]
+    assert all(torch.equal(states[0], s) for s in states[1:])
+    assert net._tome_info["size"] == (8, 8)

@@ -141,8 +141,9 @@ def compute_merge(module: torch.nn.Module, x: torch.Tensor, tome_info: Dict[str,
 
     def m(_x: torch.Tensor, **kwarg) -> torch.Tensor:
         return merged
-    u = plan.unmerge
-    u.plan = plan
+    def u(y: torch.Tensor, **kwarg) -> torch.Tensor:
+        return plan.unmerge(y)
+    m.plan = u.plan = plan
     return m, u, merged
 
 
