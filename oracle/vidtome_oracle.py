@@ -128,8 +128,25 @@ class Match:
         return out
 
 
+def _rowmax_first_index_f16(s32: np.ndarray):
+    """max / first arg-max of fp16(s32) along the last axis WITHOUT converting the whole matrix to fp16
+    (numpy's half conversion is slow).  Rounding is monotone, so the fp16 maximum is fp16(max s32) =: h, and
+    an element rounds to h iff it lies above the midpoint between h and its fp16 predecessor (or exactly on
+    it when h's mantissa is even: round-to-nearest-even).  Equivalent to `s32.astype(f16).argmax(-1)`;
+    tests/test_oracle_golden.py checks the equivalence."""
+    m32 = s32.max(-1)
+    h = m32.astype(np.float16)
+    prev = np.nextafter(h, np.float16(-np.inf))
+    mid = (h.astype(np.float32) + prev.astype(np.float32)) * np.float32(0.5)     # exact in fp32
+    even = (h.view(np.uint16) & 1) == 0
+    cand = s32 > mid[..., None]
+    tie = even[..., None] & (s32 == mid[..., None])
+    idx = (cand | tie).argmax(-1)
+    return h, idx
+
+
 def _match(metric: np.ndarray, a_idx: np.ndarray, b_idx: np.ndarray, ratio: float, align_batch: bool,
-           row_block: int = 4096) -> Match:
+           row_block: int = 4096, fast: bool = True) -> Match:
     """merge.py:84-117 (shared verbatim by :389-421).  The score matrix is produced in row blocks so
     that the full-size configurations fit in host memory; results are identical to the one-shot form."""
     B, N, _ = metric.shape
@@ -140,13 +157,20 @@ def _match(metric: np.ndarray, a_idx: np.ndarray, b_idx: np.ndarray, ratio: floa
     Bp = 1 if align_batch else B
     node_max = np.empty((Bp, Ns), dtype=metric.dtype)
     node_idx = np.empty((Bp, Ns), dtype=np.int64)
+    ct = _compute_dtype(metric)
+    half = metric.dtype == np.float16
+    a32, bT32 = a.astype(ct), np.ascontiguousarray(np.swapaxes(b.astype(ct), -1, -2))
     for lo in range(0, Ns, row_block):
         hi = min(Ns, lo + row_block)
-        s = scores_matmul(a[:, lo:hi], b)                                     # :87  [B, rows, Nd]
+        s = np.matmul(a32[:, lo:hi], bT32)                                    # :87  [B, rows, Nd] (fp32 accumulate)
         if align_batch:
             s = np.concatenate([s[i] for i in range(B)], axis=-1)[None]       # :96  [1, rows, B*Nd]
-        node_idx[:, lo:hi] = s.argmax(-1)                                     # :97 / :112 (first max)
-        node_max[:, lo:hi] = np.take_along_axis(s, node_idx[:, lo:hi, None], -1)[..., 0]
+        if half and fast:
+            node_max[:, lo:hi], node_idx[:, lo:hi] = _rowmax_first_index_f16(s)
+        else:
+            s = s.astype(metric.dtype)                                        # the reference's `scores` dtype
+            node_idx[:, lo:hi] = s.argmax(-1)                                 # :97 / :112 (first max)
+            node_max[:, lo:hi] = np.take_along_axis(s, node_idx[:, lo:hi, None], -1)[..., 0]
     edge_idx = stable_argsort_desc(node_max)                                  # :98 / :113
     unm_idx = edge_idx[:, r:]                                                 # :100 / :115
     src_idx = edge_idx[:, :r]                                                 # :101 / :116

@@ -1,0 +1,93 @@
+"""KD (QKV projection + flash attention + output projection, all tcgen05) against a torch fp32 reference of
+the same op (utils/pnp_utils.py:47-95 math) and against the numpy oracle.  Needs a B200."""
+import numpy as np
+import pytest
+import torch
+
+import vidtome_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_attention(x, wq, wk, wv, wo, bo, heads, scale):
+    B, L, C = x.shape
+    xf = x.float()
+    q = (xf @ wq.float().t()).half().float().view(B, L, heads, -1).transpose(1, 2)
+    k = (xf @ wk.float().t()).half().float().view(B, L, heads, -1).transpose(1, 2)
+    v = (xf @ wv.float().t()).half().float().view(B, L, heads, -1).transpose(1, 2)
+    s = (q @ k.transpose(-1, -2)) * scale
+    o = (s.softmax(-1) @ v).transpose(1, 2).reshape(B, L, C).half().float()
+    return o @ wo.float().t() + bo.float()
+
+
+@pytest.mark.parametrize("B,L,C,heads", [
+    (1, 128, 320, 8),       # one tile, head_dim 40
+    (2, 333, 320, 8),       # ragged tiles (SURVEY: F=4, T=256 -> 333 merged tokens)
+    (2, 641, 640, 8),       # head_dim 80: two 64-wide blocks
+    (2, 1332, 320, 5),      # head_dim 64 (SD2.x)
+    (2, 2561, 640, 8),      # BASELINE config 2, ds2 merged length
+    (1, 700, 1024, 8),      # head_dim 128
+])
+def test_attention_matches_fp32_reference(B, L, C, heads):
+    from vidtome_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(L)
+    x = torch.randn((B, L, C), generator=g, device="cuda").half()
+    ws = [(torch.randn((C, C), generator=g, device="cuda") / C ** 0.5).half() for _ in range(4)]
+    bo = (0.1 * torch.randn((C,), generator=g, device="cuda")).half()
+    scale = (C // heads) ** -0.5
+    y = ops.attention(x, torch.cat(ws[:3], 0).contiguous(), ws[3], bo, heads, scale)
+    ref = _ref_attention(x, ws[0], ws[1], ws[2], ws[3], bo, heads, scale)
+    err = (y.float() - ref).abs().max().item()
+    assert torch.isfinite(y).all()
+    assert err <= 1e-3 * ref.abs().max().item() + 2e-3, err      # 1e-3 relative fp16 tolerance (+ fp16 rounding of y)
+
+
+def test_attention_matches_oracle_small():
+    from vidtome_b200 import ops
+    rng = np.random.default_rng(0)
+    B, L, C, heads = 2, 200, 128, 2
+    x = rng.standard_normal((B, L, C)).astype(np.float16)
+    w = [(rng.standard_normal((C, C)) / np.sqrt(C)).astype(np.float16) for _ in range(4)]
+    bo = (0.1 * rng.standard_normal(C)).astype(np.float16)
+    want = O.attention(x, w[0], w[1], w[2], w[3], bo, heads).astype(np.float32)
+    t = lambda a: torch.from_numpy(a).cuda()
+    y = ops.attention(t(x), torch.cat([t(w[0]), t(w[1]), t(w[2])], 0).contiguous(), t(w[3]), t(bo), heads,
+                      (C // heads) ** -0.5)
+    err = np.abs(y.float().cpu().numpy() - want).max()
+    assert err <= 1e-3 * np.abs(want).max() + 2e-3, err
+
+
+def test_attention_full_size_c2_ds1_vs_sdpa():
+    """BASELINE config 2, ds1 merged length (B=2, L=10241, C=320, 8 heads x 40) against torch SDPA on the
+    same projections."""
+    from vidtome_b200 import ops
+    B, L, C, heads = 2, 10241, 320, 8
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn((B, L, C), generator=g, device="cuda").half()
+    ws = [(torch.randn((C, C), generator=g, device="cuda") / C ** 0.5).half() for _ in range(4)]
+    bo = torch.zeros((C,), device="cuda").half()
+    y = ops.attention(x, torch.cat(ws[:3], 0).contiguous(), ws[3], bo, heads, 40 ** -0.5)
+    q, k, v = [(x @ w.t()).view(B, L, heads, 40).transpose(1, 2) for w in ws[:3]]
+    o = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, L, C)
+    ref = (o @ ws[3].t()).float()
+    err = (y.float() - ref).abs().max().item()
+    assert err <= 2e-3 * ref.abs().max().item() + 2e-3, err
+
+
+def test_patched_block_uses_cuda_attention(monkeypatch):
+    """With the attention kernel enabled the patched block must not call attn1.forward."""
+    import vidtome_b200
+    from vidtome_b200 import attention
+    from vidtome_b200.skeleton import make_skeleton
+    if not attention.ENABLED:
+        pytest.skip("attention kernel not enabled")
+    net = make_skeleton("tiny", device="cuda", max_downsample=1)
+    vidtome_b200.apply_patch(net, batch_size=2)
+    calls = []
+    for blk in net.blocks:
+        orig = type(blk.attn1).forward
+        monkeypatch.setattr(type(blk.attn1), "forward", lambda self, *a, **k: calls.append(1) or orig(self, *a, **k))
+    lat = torch.randn(8, 4, 16, 16, device="cuda", dtype=torch.float16)
+    with torch.no_grad():
+        out = net(lat, 0).sample
+    assert torch.isfinite(out).all() and not calls

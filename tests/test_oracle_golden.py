@@ -153,3 +153,22 @@ def test_block_fixture_against_oracle_self_attention_section():
     # fp16 pipeline with different rounding points: compare against fp16 resolution of the output scale
     assert np.median(err) < 2e-3 * np.abs(ref).max()
     assert (err < 2e-2 * np.abs(ref).max()).mean() > 0.995
+
+
+def test_fast_f16_argmax_equals_converting_the_matrix():
+    """oracle._rowmax_first_index_f16 (no fp16 conversion of the score matrix) == astype(f16).argmax."""
+    rng = np.random.default_rng(3)
+    for trial in range(4):
+        x = (rng.standard_normal((2, 4 * 64, 64)) * (1 if trial % 2 else 1e-3)).astype(np.float16)
+        if trial >= 2:   # heavy exact ties, including values that round onto each other
+            x = np.round(x * 2) / 2
+            x[x == 0] = 0.5
+            x = x.astype(np.float16)
+        a_idx, b_idx, _, _ = O.split_indices_randframe(256, 4, 0, 4, trial % 4)
+        for align in (False, True):
+            m_fast = O._match(x, a_idx, b_idx, 0.9, align, row_block=50, fast=True)
+            m_slow = O._match(x, a_idx, b_idx, 0.9, align, row_block=4096, fast=False)
+            np.testing.assert_array_equal(m_fast.node_idx, m_slow.node_idx)
+            np.testing.assert_array_equal(m_fast.node_max.view(np.uint16) & 0x7FFF | (m_fast.node_max.view(np.uint16) & 0x8000) * (m_fast.node_max != 0),
+                                          m_slow.node_max.view(np.uint16) & 0x7FFF | (m_slow.node_max.view(np.uint16) & 0x8000) * (m_slow.node_max != 0))
+            np.testing.assert_array_equal(m_fast.src_idx, m_slow.src_idx)

@@ -84,6 +84,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar,
+                                            int32_t c0, int32_t c1, int32_t c2, int32_t c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_result_addr, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -114,6 +123,17 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]: A (fp16, two K elements per 32-bit column, row = lane) comes from
+// tensor memory — used for P*V in attention.
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
@@ -137,7 +157,17 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
       : "r"(taddr)
       : "memory");
 }
-// fp32 x 32 -> registers st (registers -> TMEM), used by attention to write P back.
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// registers -> TMEM (32 lanes x 16 columns): used by attention to write P and the rescaled O back.
 __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
@@ -166,11 +196,32 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_kmajor(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// Same tile read as an MN-major operand (the 64-element rows are the M/N direction, successive rows are
+// K): SBO = 1024 B between groups of 8 K rows, LBO = byte distance between 64-wide M/N blocks.
+// Advancing K by 16 adds 16 rows x 128 B = 2048 B to the start address.
+__device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>(1024u >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
 // Instruction descriptor for kind::f16, A/B fp16 K-major, D fp32:
 // c_format F32 (1) [4,6) | a_format F16 (0) [7,10) | b_format F16 (0) [10,13) | a/b major K (0)
 // [15],[16] | N>>3 [17,23) | M>>4 [24,29).
 __host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N) {
   return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+// Same with B read MN-major (bit 16).
+__host__ __device__ constexpr uint32_t umma_idesc_f16_bmn(uint32_t M, uint32_t N) {
+  return umma_idesc_f16(M, N) | (1u << 16);
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 // ---------------------------------------------------------------- misc

@@ -14,6 +14,21 @@ from . import _lib
 from ._lib import VtmSplit, check
 
 
+class _Stats:
+    """Launch accounting for bench.py: `launches` counts the CUDA kernels this library enqueued;
+    when `time_ka` is set, every KA launch is bracketed by CUDA events on the launching stream."""
+    launches = 0
+    time_ka = False
+    ka_events = []      # (start_event, end_event, flops, bytes)
+
+    @classmethod
+    def reset(cls, time_ka: bool = False):
+        cls.launches, cls.time_ka, cls.ka_events = 0, time_ka, []
+
+
+STATS = _Stats
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -55,6 +70,7 @@ def normalize_split(x: torch.Tensor, rowmap: Optional[torch.Tensor], split: VtmS
     check(_lib.load().vtm_normalize_split(x.data_ptr(), x.stride(0), _ptr(rowmap), map_bs, C.byref(split),
                                           B, Cc, a.data_ptr(), b.data_ptr(), _stream()),
           "vtm_normalize_split")
+    STATS.launches += 1
     return a, b
 
 
@@ -66,8 +82,17 @@ def sim_argmax(a: torch.Tensor, b: torch.Tensor, align_batch: bool, simt: bool =
     Nd = b.shape[1]
     keys = torch.empty((1 if align_batch else B, Ns), dtype=torch.int64, device=a.device)
     fn = _lib.load().vtm_sim_argmax_simt if simt else _lib.load().vtm_sim_argmax
+    ev = None
+    if STATS.time_ka:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
     check(fn(a.data_ptr(), b.data_ptr(), B, Ns, Nd, Cc, int(bool(align_batch)), keys.data_ptr(), _stream()),
           "vtm_sim_argmax")
+    if ev is not None:
+        ev[1].record()
+        STATS.ka_events.append((ev[0], ev[1], 2.0 * B * Ns * Nd * Cc,
+                                2.0 * B * (Ns + Nd) * Cc + 8.0 * keys.shape[0] * Ns))
+    STATS.launches += 1
     return keys
 
 
@@ -82,6 +107,7 @@ def topr_sort(keys: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     rank = torch.empty((Bp, Ns), dtype=torch.int32, device=keys.device)
     check(lib.vtm_topr_sort(keys.data_ptr(), Bp, Ns, edge.data_ptr(), rank.data_ptr(), ws.data_ptr(),
                             ws_bytes, _stream()), "vtm_topr_sort")
+    STATS.launches += 6
     return edge, rank
 
 
@@ -100,6 +126,7 @@ def compose_maps(split: VtmSplit, r: int, keys: torch.Tensor, edge: torch.Tensor
     check(_lib.load().vtm_compose_maps(C.byref(split), r, Ns, nd, Bp, keys.data_ptr(), edge.data_ptr(),
                                        rank.data_ptr(), _ptr(mu_in), _ptr(pi_in), pi_offset, N0,
                                        mu_out.data_ptr(), pi_out.data_ptr(), _stream()), "vtm_compose_maps")
+    STATS.launches += 1
     return mu_out, pi_out
 
 
@@ -115,6 +142,7 @@ def decode_match(keys: torch.Tensor, edge: torch.Tensor, Nd: int, r: int, want_n
     check(_lib.load().vtm_decode_match(keys.data_ptr(), edge.data_ptr(), Bp, Ns, Nd, r, unm.data_ptr(),
                                        src.data_ptr(), dst.data_ptr(), _ptr(nmax), _ptr(nidx), _stream()),
           "vtm_decode_match")
+    STATS.launches += 1
     return (unm, src, dst, nmax, nidx) if want_node else (unm, src, dst)
 
 
@@ -132,6 +160,7 @@ def gather_rows(x: torch.Tensor, row_map: Optional[torch.Tensor], L: Optional[in
         out = torch.empty((B, L, Cc), dtype=torch.float16, device=x.device)
     check(_lib.load().vtm_gather_rows(x.data_ptr(), x.stride(0), _ptr(row_map), map_bs, B, L, Cc,
                                       out.data_ptr(), out.stride(0), _stream()), "vtm_gather_rows")
+    STATS.launches += 1
     return out
 
 
@@ -147,6 +176,7 @@ def unmerge_add(y: torch.Tensor, row_map: torch.Tensor, resid: Optional[torch.Te
     out = torch.empty((B, N, Cc), dtype=torch.float16, device=y.device)
     check(_lib.load().vtm_unmerge_add(y.data_ptr(), y.stride(0), row_map.data_ptr(), map_bs, _ptr(resid),
                                       B, N, Cc, out.data_ptr(), _stream()), "vtm_unmerge_add")
+    STATS.launches += 1
     return out
 
 
@@ -161,6 +191,7 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
         _require(bias, torch.float16, "bias")
     check(_lib.load().vtm_linear_f16(a.data_ptr(), w.data_ptr(), _ptr(bias), M, N, K, d.data_ptr(), N, _stream()),
           "vtm_linear_f16")
+    STATS.launches += 1
     return d
 
 
@@ -177,6 +208,7 @@ def attention(x: torch.Tensor, w_qkv: torch.Tensor, w_o: torch.Tensor, b_o: Opti
     y = torch.empty_like(x)
     check(lib.vtm_attention(x.data_ptr(), w_qkv.data_ptr(), w_o.data_ptr(), _ptr(b_o), B, L, Cc, heads,
                             float(scale), y.data_ptr(), ws.data_ptr(), ws_bytes, _stream()), "vtm_attention")
+    STATS.launches += 3
     return y
 
 

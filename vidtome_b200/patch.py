@@ -22,8 +22,8 @@ import torch
 
 from . import merge, ops
 from ._lib import VtmSplit
-from .utils import (func_warper, init_generator, isinstance_str, join_frame, join_warper, split_frame,
-                    split_warper)
+from .utils import (draw_scalar, func_warper, init_generator, isinstance_str, join_frame, join_warper,
+                    split_frame, split_warper)
 
 
 @dataclass
@@ -77,8 +77,8 @@ def build_merge_plan(module: torch.nn.Module, x: torch.Tensor, tome_info: Dict[s
             unm += (L - unm) // curF                                         # merge.py:45-46 (no draw)
         else:
             stride = min(args["target_stride"], curF)                        # merge.py:55
-            randf = int(torch.randint(0, stride, torch.Size([1]), generator=generator,
-                                      device=generator.device).item())      # merge.py:56-57
+            randf = int(draw_scalar(generator, lambda: torch.randint(
+                0, stride, torch.Size([1]), generator=generator, device=generator.device)))  # merge.py:56-57
             randfs.append(randf)
             split = VtmSplit.local(L, unm, curF, args["target_stride"], randf)
             m = merge.match_level(table, mu, split, ratio, align)            # patch.py:45-46
@@ -96,7 +96,8 @@ def build_merge_plan(module: torch.nn.Module, x: torch.Tensor, tome_info: Dict[s
         local_tokens = ops.gather_rows(table, mu)                            # merged local tokens [B, L, C]
         g = getattr(module, "global_tokens", None)
         if g is not None:                                                    # patch.py:60
-            coin = float(torch.rand(1, generator=generator, device=generator.device).item())  # patch.py:62
+            coin = float(draw_scalar(generator, lambda: torch.rand(
+                1, generator=generator, device=generator.device)))                            # patch.py:62
             g = g.to(local_tokens).contiguous()                              # patch.py:65,70
             Lg = g.shape[1]
             if coin > args["global_rand"]:

@@ -52,3 +52,23 @@ def split_warper(fsize):
     def fn(x):
         return split_frame(x, fsize)
     return fn
+
+
+_rng_streams = {}
+
+
+def draw_scalar(generator: torch.Generator, fn):
+    """Evaluate `fn()` (a one-element torch.randint / torch.rand call on `generator`) and return its
+    Python value.  The reference does this on the current stream, so reading the value back waits for all
+    queued compute (merge.py:56-64 boolean-mask indexing, patch.py:62 `if torch.rand(...) > ...`).  The draw
+    depends only on the generator state, never on data, so it is issued on a small side stream instead:
+    the read-back then synchronises that stream only and the main stream keeps running.  Draw order and
+    values are unchanged (Philox offsets are advanced on the host at call time)."""
+    if generator.device.type != "cuda":
+        return fn().item()
+    dev = generator.device
+    st = _rng_streams.get(dev)
+    if st is None:
+        st = _rng_streams[dev] = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(st):
+        return fn().item()
