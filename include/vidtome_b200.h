@@ -86,6 +86,18 @@ int vtm_normalize_split(const void* x_dev, int64_t x_batch_stride, const int32_t
                         void* a_out_dev, void* b_out_dev, void* stream);
 
 /*
+ * K0 with the block's LayerNorm fused in front: rows are read from the RAW hidden states, normalised with
+ * (ln_weight, ln_bias, ln_eps) exactly as `self.norm1(hidden_states)` does (vidtome/patch.py:146; torch
+ * half semantics: fp32 statistics, y = gamma * (rstd * (x - mean)) + beta rounded to fp16) and then handled
+ * as in vtm_normalize_split.  norm1's output is never written to memory.  ln_weight_dev == NULL disables
+ * the LayerNorm (== vtm_normalize_split); ln_bias_dev may be NULL.
+ */
+int vtm_normalize_split_ln(const void* x_dev, int64_t x_batch_stride, const int32_t* rowmap_dev,
+                           int64_t rowmap_batch_stride, const vtm_split_t* split, int32_t B, int32_t C,
+                           const void* ln_weight_dev, const void* ln_bias_dev, float ln_eps, void* a_out_dev,
+                           void* b_out_dev, void* stream);
+
+/*
  * KA — fused similarity + row arg-max on tcgen05 tensor cores.  Replaces
  * `scores = a @ b.transpose(-1, -2)` and `scores.max(dim=-1)` (vidtome/merge.py:87,112 and :392,416)
  * and, with align_batch != 0, `torch.cat([*scores], dim=-1)` + max (merge.py:93-97, :398-401).
@@ -156,6 +168,12 @@ int vtm_decode_match(const uint64_t* keys_dev, const int32_t* edge_dev, int32_t 
 int vtm_gather_rows(const void* x_dev, int64_t x_batch_stride, const int32_t* map_dev,
                     int64_t map_batch_stride, int32_t B, int32_t L, int32_t C, void* y_dev,
                     int64_t y_batch_stride, void* stream);
+
+/* KC with norm1 fused: y[b, i, :] = LayerNorm(x[b, map[b, i], :]) — the merged tokens that feed attn1,
+ * computed from the raw hidden states (only the L kept rows are ever normalised). */
+int vtm_gather_rows_ln(const void* x_dev, int64_t x_batch_stride, const int32_t* map_dev,
+                       int64_t map_batch_stride, int32_t B, int32_t L, int32_t C, const void* ln_weight_dev,
+                       const void* ln_bias_dev, float ln_eps, void* y_dev, int64_t y_batch_stride, void* stream);
 
 /*
  * KE — unmerge gather fused with the residual add: out[b, p, :] = y[b, map[b, p], :] + resid[b, p, :].

@@ -211,3 +211,31 @@ def test_linear_f16(M, N, K, bias):
         ref = ref + bb.float()
     err = (d.float() - ref).abs().max().item()
     assert err <= 1e-3 * max(1.0, ref.abs().max().item()) + 1e-3  # fp16 output rounding, rel 1e-3
+
+
+# --------------------------------------------------------------------------- fused LayerNorm (norm1)
+@pytest.mark.parametrize("C", [320, 640, 1280, 128])
+def test_fused_layernorm_in_k0_and_kc(C):
+    """K0 / KC with norm1 fused == torch LayerNorm (fp16, the module the reference calls at patch.py:146)
+    followed by the plain kernels; at most one fp16 ulp apart (different fp32 summation order)."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(C)
+    B, F, T = 2, 4, 96
+    N = F * T
+    x = (torch.randn((B, N, C), generator=g, device="cuda") * 2 + 0.3).half()
+    ln = torch.nn.LayerNorm(C).cuda().half()
+    with torch.no_grad():
+        ln.weight.copy_(1 + 0.2 * torch.randn(C, generator=g, device="cuda"))
+        ln.bias.copy_(0.1 * torch.randn(C, generator=g, device="cuda"))
+        y = ln(x)
+    sp = _split(N, 0, F, 4, 1)
+    a0, b0 = ops.normalize_split(y, None, sp)
+    a1, b1 = ops.normalize_split(x, None, sp, ln=(ln.weight.data, ln.bias.data, ln.eps))
+    for got, want in ((a1, a0), (b1, b0)):
+        d = _ulp_diff_f16(got.cpu().numpy(), want.cpu().numpy())
+        assert d.max() <= 2 and (d > 0).mean() < 0.02
+    mu = torch.randint(0, N, (B, 123), generator=g, device="cuda", dtype=torch.int32)
+    m0 = ops.gather_rows(y, mu)
+    m1 = ops.gather_rows(x, mu, ln=(ln.weight.data, ln.bias.data, ln.eps))
+    d = _ulp_diff_f16(m1.cpu().numpy(), m0.cpu().numpy())
+    assert d.max() <= 1 and (d > 0).mean() < 0.01

@@ -258,3 +258,26 @@ def test_patched_block_matches_reference_block(name, strict, monkeypatch):
         assert (rel < 1e-2).float().mean() > 0.90
     vidtome_b200.remove_patch(net)
     assert type(net.block).__name__ == "BasicTransformerBlock"
+
+
+def test_fused_layernorm_block_equals_unfused_block():
+    """The LayerNorm-fused block (norm1 inside K0/KC) and the unfused block (torch LayerNorm, then the merge
+    kernels) agree: same merged length, and outputs equal to fp16 tolerance on (almost) all tokens."""
+    import vidtome_b200
+    from vidtome_b200 import patch
+    from vidtome_b200.skeleton import make_skeleton
+    outs = []
+    for fuse in (True, False):
+        patch.FUSE_LAYERNORM = fuse
+        try:
+            net = make_skeleton("tiny", device="cuda", max_downsample=1, seed=7)
+            vidtome_b200.apply_patch(net, batch_size=2, local_merge_ratio=1.0)
+            torch.manual_seed(3)
+            torch.cuda.manual_seed(3)
+            lat = torch.randn(2 * 4, 4, 16, 16, device="cuda", dtype=torch.float16)
+            with torch.no_grad():
+                outs.append(net(lat, 0).sample.float())
+        finally:
+            patch.FUSE_LAYERNORM = True
+    err = (outs[0] - outs[1]).abs()
+    assert (err <= 2e-2 * outs[1].abs().max()).float().mean() > 0.98

@@ -109,6 +109,27 @@ def bench_linear(M, N, K, iters):
                       "cublas_tflops": round(flops / med_t / 1e9, 1)}), flush=True)
 
 
+def bench_attention(B, L, C, heads, iters):
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn((B, L, C), generator=g, device="cuda").half()
+    ws = [(torch.randn((C, C), generator=g, device="cuda") / C ** 0.5).half() for _ in range(4)]
+    wqkv = torch.cat(ws[:3], 0).contiguous()
+    bo = torch.zeros(C, device="cuda").half()
+    d = C // heads
+    med, _ = time_ms(lambda: ops.attention(x, wqkv, ws[3], bo, heads, d ** -0.5), iters)
+
+    def sdpa():
+        q, k, v = [torch.nn.functional.linear(x, w).view(B, L, heads, d).transpose(1, 2) for w in ws[:3]]
+        o = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, L, C)
+        return torch.nn.functional.linear(o, ws[3], bo)
+    med_t, _ = time_ms(sdpa, iters)
+    qkv = ops.linear(x.view(B * L, C), wqkv)
+    flops = 4.0 * B * L * L * C + 8.0 * B * L * C * C
+    print(json.dumps({"kernel": "KD attention (qkv+flash+out)", "B": B, "L": L, "C": C, "heads": heads,
+                      "ms": round(med, 4), "tflops": round(flops / med / 1e9, 1), "torch_sdpa_path_ms": round(med_t, 4),
+                      "speedup_vs_torch": round(med_t / med, 2)}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
@@ -121,6 +142,8 @@ def main():
     bench_sim_argmax(2, 49152, 16384, 320, True, args.iters)
     bench_rows(2, 16, 4096, 320, args.iters)
     bench_rows(2, 16, 1024, 640, args.iters)
+    bench_attention(2, 10241, 320, 8, args.iters)
+    bench_attention(2, 2561, 640, 8, args.iters)
     bench_linear(20482, 960, 320, args.iters)
     bench_linear(5122, 1920, 640, args.iters)
     if args.quick:

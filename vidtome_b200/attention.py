@@ -12,7 +12,7 @@ import torch
 from . import _lib, ops
 
 # Switched on once the tcgen05 attention kernel is built into the library.
-ENABLED = False
+ENABLED = True
 
 
 def _packed_weights(attn: torch.nn.Module, like: torch.Tensor):

@@ -1,15 +1,22 @@
 // HBM-bound row kernels: K0 normalise+split, KC merge gather, KE unmerge gather + residual add.
-// All three move whole token rows (C fp16, C % 8 == 0) with 16-byte vector accesses; one warp owns
-// one row at a time so that the row-index lookup is done once per row and the accesses of a warp are
-// contiguous.  Grids are sized as a multiple of the SM count and stride over rows.
+// All three move whole token rows (C fp16, C % 8 == 0) with 16-byte vector accesses.  A row is owned by
+// a group of G lanes (G = 8/16/32 chosen so that each lane holds <= 5..8 vectors of the row in registers),
+// so a warp works on 32/G rows at once with all their loads in flight, the row-index lookup is done once
+// per row, and reductions over a row are G-lane shuffles.  Grids are a multiple of the SM count and
+// stride over rows.
+//
+// K0 and KC can apply the block's LayerNorm (norm1, vidtome/patch.py:146) on the fly to the rows they read:
+// the row is already in registers, so norm1's output never has to be written to and re-read from HBM.
+// The fused LayerNorm follows torch's half kernel: statistics in fp32, y = gamma * (rstd * (x - mean)) + beta
+// in fp32, rounded to fp16 — and only then used (K0 goes on to L2-normalise the rounded row, as
+// merge.py:84 does with norm1's fp16 output).
 #include "common.cuh"
 #include "ptx.cuh"
 
 namespace vtm {
 namespace {
 
-constexpr int ROW_THREADS = 256;  // 8 warps per CTA
-constexpr int MAX_VEC_PER_LANE = 8;  // supports C up to 32 * 8 * 8 = 2048
+constexpr int ROW_THREADS = 256;
 
 __device__ __forceinline__ uint4 ld_nc_16(const void* p) {
   uint4 r;
@@ -18,126 +25,199 @@ __device__ __forceinline__ uint4 ld_nc_16(const void* p) {
                : "l"(p));
   return r;
 }
+__device__ __forceinline__ uint4 ld_16(const void* p) { return *reinterpret_cast<const uint4*>(p); }
 __device__ __forceinline__ void st_16(void* p, const uint4& v) {
   asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y),
                "r"(v.z), "r"(v.w)
                : "memory");
 }
 
-// ------------------------------------------------------------------ K0: normalise + split
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+struct LnParams {
+  const __half* w;   // gamma [C] (nullptr = no LayerNorm)
+  const __half* b;   // beta  [C] (may be nullptr)
+  float eps;
+};
+
+// In-register LayerNorm of one row held as P vectors per lane by a G-lane group (torch half semantics).
+template <int G, int P>
+__device__ __forceinline__ void layer_norm_row(uint4 (&v)[P], int sub, int vecs, int C, const LnParams& ln) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    if (sub + G * i < vecs) {
+      const __half2* h = reinterpret_cast<const __half2*>(&v[i]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(h[e]);
+        s += f.x + f.y;
+      }
+    }
+  }
+  const float mean = group_sum<G>(s) / static_cast<float>(C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    if (sub + G * i < vecs) {
+      const __half2* h = reinterpret_cast<const __half2*>(&v[i]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(h[e]);
+        q = fmaf(f.x - mean, f.x - mean, q);
+        q = fmaf(f.y - mean, f.y - mean, q);
+      }
+    }
+  }
+  const float rstd = rsqrtf(group_sum<G>(q) / static_cast<float>(C) + ln.eps);
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    const int vi = sub + G * i;
+    if (vi < vecs) {
+      const uint4 gw = ld_16(ln.w + vi * 8);
+      uint4 gb = make_uint4(0, 0, 0, 0);
+      if (ln.b) gb = ld_16(ln.b + vi * 8);
+      __half2* h = reinterpret_cast<__half2*>(&v[i]);
+      const __half2* w2 = reinterpret_cast<const __half2*>(&gw);
+      const __half2* b2 = reinterpret_cast<const __half2*>(&gb);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(h[e]);
+        const float2 wf = __half22float2(w2[e]);
+        const float2 bf = __half22float2(b2[e]);
+        h[e] = __floats2half2_rn(wf.x * (rstd * (f.x - mean)) + bf.x, wf.y * (rstd * (f.y - mean)) + bf.y);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ K0: [LayerNorm] + L2-normalise + split
 // merge.py:84 `metric = metric / metric.norm(dim=-1, keepdim=True)`; merge.py:76-85 split().
 // torch half semantics: norm accumulates in fp32 and is rounded to fp16; the division is carried out
 // in fp32 on the fp16-rounded norm and rounded to fp16.
+template <int G, int P>
 __global__ void __launch_bounds__(ROW_THREADS)
 normalize_split_kernel(const __half* __restrict__ x, long long x_bs, const int* __restrict__ rowmap,
-                       long long map_bs, Split sp, int B, int C, __half* __restrict__ a_out,
+                       long long map_bs, Split sp, int B, int C, LnParams ln, __half* __restrict__ a_out,
                        __half* __restrict__ b_out) {
+  constexpr int RPW = 32 / G;                       // rows per warp
   const int lane = threadIdx.x & 31;
-  const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+  const int sub = lane % G, grp = lane / G;
+  const long long warp_id = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   const int vecs = C >> 3;
   const long long rows_per_b = static_cast<long long>(sp.Ns) + sp.Nd;
   const long long total = rows_per_b * B;
-  for (long long o = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; o < total;
-       o += warps_per_grid) {
-    const int b = static_cast<int>(o / rows_per_b);
-    const int q = static_cast<int>(o - b * rows_per_b);
-    int pos;
-    __half* dst;
-    if (q < sp.Ns) {
-      pos = src_pos(sp, q);
-      dst = a_out + (static_cast<long long>(b) * sp.Ns + q) * C;
-    } else {
-      pos = dst_pos(sp, q - sp.Ns);
-      dst = b_out + (static_cast<long long>(b) * sp.Nd + (q - sp.Ns)) * C;
+  for (long long o0 = warp_id * RPW; o0 < total; o0 += n_warps * RPW) {
+    const long long o = o0 + grp;
+    const bool live = o < total;
+    const __half* src = x;
+    __half* dst = a_out;
+    if (live) {
+      const int b = static_cast<int>(o / rows_per_b);
+      const int q = static_cast<int>(o - b * rows_per_b);
+      int pos;
+      if (q < sp.Ns) {
+        pos = src_pos(sp, q);
+        dst = a_out + (static_cast<long long>(b) * sp.Ns + q) * C;
+      } else {
+        pos = dst_pos(sp, q - sp.Ns);
+        dst = b_out + (static_cast<long long>(b) * sp.Nd + (q - sp.Ns)) * C;
+      }
+      const int row = rowmap ? rowmap[b * map_bs + pos] : pos;
+      src = x + b * x_bs + static_cast<long long>(row) * C;
     }
-    const int row = rowmap ? rowmap[b * map_bs + pos] : pos;
-    const __half* src = x + b * x_bs + static_cast<long long>(row) * C;
-
-    uint4 v[MAX_VEC_PER_LANE];
+    uint4 v[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+      v[i] = make_uint4(0, 0, 0, 0);
+      if (live && sub + G * i < vecs) v[i] = ld_nc_16(src + (sub + G * i) * 8);
+    }
+    if (ln.w) layer_norm_row<G, P>(v, sub, vecs, C, ln);
     float ss = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAX_VEC_PER_LANE; ++i) {
-      const int vi = lane + 32 * i;
-      if (vi < vecs) {
-        v[i] = ld_nc_16(src + vi * 8);
-        const __half2* h = reinterpret_cast<const __half2*>(&v[i]);
+    for (int i = 0; i < P; ++i) {
+      const __half2* h = reinterpret_cast<const __half2*>(&v[i]);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 f = __half22float2(h[e]);
-          ss = fmaf(f.x, f.x, ss);
-          ss = fmaf(f.y, f.y, ss);
-        }
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(h[e]);
+        ss = fmaf(f.x, f.x, ss);
+        ss = fmaf(f.y, f.y, ss);
       }
     }
-    ss = warp_sum(ss);
+    ss = group_sum<G>(ss);
     const float nrm = __half2float(__float2half_rn(sqrtf(ss)));
 #pragma unroll
-    for (int i = 0; i < MAX_VEC_PER_LANE; ++i) {
-      const int vi = lane + 32 * i;
-      if (vi < vecs) {
+    for (int i = 0; i < P; ++i) {
+      if (live && sub + G * i < vecs) {
         __half2* h = reinterpret_cast<__half2*>(&v[i]);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float2 f = __half22float2(h[e]);
           h[e] = __halves2half2(__float2half_rn(f.x / nrm), __float2half_rn(f.y / nrm));
         }
-        st_16(dst + vi * 8, v[i]);
+        st_16(dst + (sub + G * i) * 8, v[i]);
       }
     }
   }
 }
 
 // ------------------------------------------------------------------ KC / KE: row gathers
-// y[b, i, :] = x[b, map[b, i], :] (+ resid[b, i, :]).  Thread-per-16-bytes, 4 rows in flight.
-template <bool ADD>
+// y[b, i, :] = [LN](x[b, map[b, i], :]) (+ resid[b, i, :]).
+template <int G, int P, bool ADD>
 __global__ void __launch_bounds__(ROW_THREADS)
 gather_rows_kernel(const __half* __restrict__ x, long long x_bs, const int* __restrict__ map, long long map_bs,
-                   const __half* __restrict__ resid, int B, int L, int C, __half* __restrict__ y,
+                   const __half* __restrict__ resid, int B, int L, int C, LnParams ln, __half* __restrict__ y,
                    long long y_bs) {
+  constexpr int RPW = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % G, grp = lane / G;
+  const long long warp_id = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   const int vecs = C >> 3;
-  const long long total = static_cast<long long>(B) * L * vecs;
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  constexpr int U = 4;
-  for (long long t0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t0 < total;
-       t0 += stride * U) {
-    uint4 v[U], rr[U];
-    long long oidx[U];
+  const long long total = static_cast<long long>(B) * L;
+  for (long long o0 = warp_id * RPW; o0 < total; o0 += n_warps * RPW) {
+    const long long o = o0 + grp;
+    const bool live = o < total;
+    const __half* src = x;
+    const __half* rs = resid;
+    __half* dst = y;
+    if (live) {
+      const int b = static_cast<int>(o / L);
+      const int i = static_cast<int>(o - static_cast<long long>(b) * L);
+      const int srow = map ? map[b * map_bs + i] : i;
+      src = x + b * x_bs + static_cast<long long>(srow) * C;
+      dst = y + b * y_bs + static_cast<long long>(i) * C;
+      if (ADD) rs = resid + (static_cast<long long>(b) * L + i) * C;
+    }
+    uint4 v[P], rr[P];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long t = t0 + u * stride;
-      oidx[u] = -1;
-      if (t < total) {
-        const long long rowg = t / vecs;
-        const int vi = static_cast<int>(t - rowg * vecs);
-        const int b = static_cast<int>(rowg / L);
-        const int i = static_cast<int>(rowg - static_cast<long long>(b) * L);
-        const int srow = map ? map[b * map_bs + i] : i;
-        v[u] = ld_nc_16(x + b * x_bs + static_cast<long long>(srow) * C + vi * 8);
-        oidx[u] = b * y_bs + static_cast<long long>(i) * C + vi * 8;
-        if (ADD) rr[u] = ld_nc_16(resid + (static_cast<long long>(b) * L + i) * C + vi * 8);
+    for (int i = 0; i < P; ++i) {
+      v[i] = make_uint4(0, 0, 0, 0);
+      if (live && sub + G * i < vecs) {
+        v[i] = ld_nc_16(src + (sub + G * i) * 8);
+        if (ADD) rr[i] = ld_nc_16(rs + (sub + G * i) * 8);
       }
     }
+    if (!ADD && ln.w) layer_norm_row<G, P>(v, sub, vecs, C, ln);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (oidx[u] >= 0) {
+    for (int i = 0; i < P; ++i) {
+      if (live && sub + G * i < vecs) {
         if (ADD) {
-          __half2* a = reinterpret_cast<__half2*>(&v[u]);
-          const __half2* r2 = reinterpret_cast<const __half2*>(&rr[u]);
+          __half2* a = reinterpret_cast<__half2*>(&v[i]);
+          const __half2* r2 = reinterpret_cast<const __half2*>(&rr[i]);
 #pragma unroll
           for (int e = 0; e < 4; ++e) a[e] = __hadd2(a[e], r2[e]);
         }
-        st_16(y + oidx[u], v[u]);
+        st_16(dst + (sub + G * i) * 8, v[i]);
       }
     }
   }
-}
-
-int grid_for(long long work_items, int per_block, int sms, int blocks_per_sm) {
-  long long need = (work_items + per_block - 1) / per_block;
-  long long cap = static_cast<long long>(sms) * blocks_per_sm;
-  if (need < 1) need = 1;
-  if (need > cap) need = cap;  // multiple of the SM count when saturated
-  return static_cast<int>(need);
 }
 
 int sm_count(int* sms) {
@@ -147,45 +227,87 @@ int sm_count(int* sms) {
   return cuda_rc(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev));
 }
 
+int grid_for_rows(long long rows, int rows_per_warp, int sms) {
+  const long long warps = (rows + rows_per_warp - 1) / rows_per_warp;
+  long long blocks = (warps + (ROW_THREADS / 32) - 1) / (ROW_THREADS / 32);
+  const long long cap = static_cast<long long>(sms) * 8;   // 8 CTAs of 256 threads per SM
+  if (blocks < 1) blocks = 1;
+  if (blocks > cap) blocks = cap;
+  return static_cast<int>(blocks);
+}
+
+// (G, P) for a row of `vecs` 16-byte vectors: G lanes x P vectors per lane >= vecs
+#define VTM_DISPATCH_GP(vecs, CALL)                 \
+  if ((vecs) <= 8 * 5) { CALL(8, 5) }               \
+  else if ((vecs) <= 16 * 5) { CALL(16, 5) }        \
+  else if ((vecs) <= 32 * 5) { CALL(32, 5) }        \
+  else { CALL(32, 8) }
+
 }  // namespace
 }  // namespace vtm
 
-extern "C" int vtm_normalize_split(const void* x_dev, int64_t x_batch_stride, const int32_t* rowmap_dev,
-                                   int64_t rowmap_batch_stride, const vtm_split_t* split, int32_t B,
-                                   int32_t C, void* a_out_dev, void* b_out_dev, void* stream_) {
+extern "C" int vtm_normalize_split_ln(const void* x_dev, int64_t x_batch_stride, const int32_t* rowmap_dev,
+                                      int64_t rowmap_batch_stride, const vtm_split_t* split, int32_t B,
+                                      int32_t C, const void* ln_weight_dev, const void* ln_bias_dev, float ln_eps,
+                                      void* a_out_dev, void* b_out_dev, void* stream_) {
   using namespace vtm;
   Split sp;
   int rc = make_split(split, &sp);
   if (rc) return rc;
   if (!x_dev || (sp.Ns > 0 && !a_out_dev) || (sp.Nd > 0 && !b_out_dev)) return VTM_E_NULL;
-  if (B <= 0 || C <= 0 || (C % 8) != 0 || C > 32 * 8 * MAX_VEC_PER_LANE) return VTM_E_SHAPE;
+  if (B <= 0 || C <= 0 || (C % 8) != 0 || C > 32 * 8 * 8) return VTM_E_SHAPE;
   int sms = 0;
   rc = sm_count(&sms);
   if (rc) return rc;
   const long long rows = (static_cast<long long>(sp.Ns) + sp.Nd) * B;
-  const int grid = grid_for(rows, ROW_THREADS / 32, sms, 8);
-  normalize_split_kernel<<<grid, ROW_THREADS, 0, static_cast<cudaStream_t>(stream_)>>>(
-      static_cast<const __half*>(x_dev), x_batch_stride, rowmap_dev, rowmap_batch_stride, sp, B, C,
+  const int vecs = C / 8;
+  LnParams ln{static_cast<const __half*>(ln_weight_dev), static_cast<const __half*>(ln_bias_dev), ln_eps};
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+#define CALL(G, P)                                                                                          \
+  normalize_split_kernel<G, P><<<grid_for_rows(rows, 32 / G, sms), ROW_THREADS, 0, st>>>(                   \
+      static_cast<const __half*>(x_dev), x_batch_stride, rowmap_dev, rowmap_batch_stride, sp, B, C, ln,     \
       static_cast<__half*>(a_out_dev), static_cast<__half*>(b_out_dev));
+  VTM_DISPATCH_GP(vecs, CALL)
+#undef CALL
+  return launch_rc();
+}
+
+extern "C" int vtm_normalize_split(const void* x_dev, int64_t x_batch_stride, const int32_t* rowmap_dev,
+                                   int64_t rowmap_batch_stride, const vtm_split_t* split, int32_t B,
+                                   int32_t C, void* a_out_dev, void* b_out_dev, void* stream_) {
+  return vtm_normalize_split_ln(x_dev, x_batch_stride, rowmap_dev, rowmap_batch_stride, split, B, C, nullptr,
+                                nullptr, 0.f, a_out_dev, b_out_dev, stream_);
+}
+
+extern "C" int vtm_gather_rows_ln(const void* x_dev, int64_t x_batch_stride, const int32_t* map_dev,
+                                  int64_t map_batch_stride, int32_t B, int32_t L, int32_t C,
+                                  const void* ln_weight_dev, const void* ln_bias_dev, float ln_eps, void* y_dev,
+                                  int64_t y_batch_stride, void* stream_) {
+  using namespace vtm;
+  if (!x_dev || !y_dev) return VTM_E_NULL;
+  if (B <= 0 || L < 0 || C <= 0 || (C % 8) != 0 || C > 32 * 8 * 8) return VTM_E_SHAPE;
+  if (L == 0) return VTM_OK;
+  int sms = 0;
+  int rc = sm_count(&sms);
+  if (rc) return rc;
+  const long long rows = static_cast<long long>(B) * L;
+  const int vecs = C / 8;
+  LnParams ln{static_cast<const __half*>(ln_weight_dev), static_cast<const __half*>(ln_bias_dev), ln_eps};
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+#define CALL(G, P)                                                                                       \
+  gather_rows_kernel<G, P, false><<<grid_for_rows(rows, 32 / G, sms), ROW_THREADS, 0, st>>>(             \
+      static_cast<const __half*>(x_dev), x_batch_stride, map_dev, map_batch_stride, nullptr, B, L, C, ln, \
+      static_cast<__half*>(y_dev), y_batch_stride);
+  VTM_DISPATCH_GP(vecs, CALL)
+#undef CALL
   return launch_rc();
 }
 
 extern "C" int vtm_gather_rows(const void* x_dev, int64_t x_batch_stride, const int32_t* map_dev,
                                int64_t map_batch_stride, int32_t B, int32_t L, int32_t C, void* y_dev,
                                int64_t y_batch_stride, void* stream_) {
-  using namespace vtm;
-  if (!x_dev || !y_dev) return VTM_E_NULL;
-  if (B <= 0 || L < 0 || C <= 0 || (C % 8) != 0) return VTM_E_SHAPE;
-  if (L == 0) return VTM_OK;
-  int sms = 0;
-  int rc = sm_count(&sms);
-  if (rc) return rc;
-  const long long items = static_cast<long long>(B) * L * (C / 8);
-  const int grid = grid_for(items, ROW_THREADS * 4, sms, 8);
-  gather_rows_kernel<false><<<grid, ROW_THREADS, 0, static_cast<cudaStream_t>(stream_)>>>(
-      static_cast<const __half*>(x_dev), x_batch_stride, map_dev, map_batch_stride, nullptr, B, L, C,
-      static_cast<__half*>(y_dev), y_batch_stride);
-  return launch_rc();
+  return vtm_gather_rows_ln(x_dev, x_batch_stride, map_dev, map_batch_stride, B, L, C, nullptr, nullptr, 0.f,
+                            y_dev, y_batch_stride, stream_);
 }
 
 extern "C" int vtm_unmerge_add(const void* y_dev, int64_t y_batch_stride, const int32_t* map_dev,
@@ -193,22 +315,30 @@ extern "C" int vtm_unmerge_add(const void* y_dev, int64_t y_batch_stride, const 
                                int32_t C, void* out_dev, void* stream_) {
   using namespace vtm;
   if (!y_dev || !out_dev || !map_dev) return VTM_E_NULL;
-  if (B <= 0 || N < 0 || C <= 0 || (C % 8) != 0) return VTM_E_SHAPE;
+  if (B <= 0 || N < 0 || C <= 0 || (C % 8) != 0 || C > 32 * 8 * 8) return VTM_E_SHAPE;
   if (N == 0) return VTM_OK;
   int sms = 0;
   int rc = sm_count(&sms);
   if (rc) return rc;
-  const long long items = static_cast<long long>(B) * N * (C / 8);
-  const int grid = grid_for(items, ROW_THREADS * 4, sms, 8);
+  const long long rows = static_cast<long long>(B) * N;
+  const int vecs = C / 8;
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   const long long out_bs = static_cast<long long>(N) * C;
-  if (resid_dev)
-    gather_rows_kernel<true><<<grid, ROW_THREADS, 0, st>>>(
-        static_cast<const __half*>(y_dev), y_batch_stride, map_dev, map_batch_stride,
-        static_cast<const __half*>(resid_dev), B, N, C, static_cast<__half*>(out_dev), out_bs);
-  else
-    gather_rows_kernel<false><<<grid, ROW_THREADS, 0, st>>>(
-        static_cast<const __half*>(y_dev), y_batch_stride, map_dev, map_batch_stride, nullptr, B, N, C,
-        static_cast<__half*>(out_dev), out_bs);
+  LnParams ln{nullptr, nullptr, 0.f};
+  if (resid_dev) {
+#define CALL(G, P)                                                                                          \
+  gather_rows_kernel<G, P, true><<<grid_for_rows(rows, 32 / G, sms), ROW_THREADS, 0, st>>>(                 \
+      static_cast<const __half*>(y_dev), y_batch_stride, map_dev, map_batch_stride,                         \
+      static_cast<const __half*>(resid_dev), B, N, C, ln, static_cast<__half*>(out_dev), out_bs);
+    VTM_DISPATCH_GP(vecs, CALL)
+#undef CALL
+  } else {
+#define CALL(G, P)                                                                                          \
+  gather_rows_kernel<G, P, false><<<grid_for_rows(rows, 32 / G, sms), ROW_THREADS, 0, st>>>(                \
+      static_cast<const __half*>(y_dev), y_batch_stride, map_dev, map_batch_stride, nullptr, B, N, C, ln,   \
+      static_cast<__half*>(out_dev), out_bs);
+    VTM_DISPATCH_GP(vecs, CALL)
+#undef CALL
+  }
   return launch_rc();
 }

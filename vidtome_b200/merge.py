@@ -66,11 +66,12 @@ def _check_metric(metric: torch.Tensor) -> None:
 
 
 def match_level(table: torch.Tensor, rowmap: Optional[torch.Tensor], split: VtmSplit, ratio: float,
-                align_batch: bool) -> LevelMatch:
+                align_batch: bool, ln=None) -> LevelMatch:
     """K0 + KA + KB1 for one level.  `table` [B, N0, C] fp16 holds the level-0 tokens, `rowmap`
-    ([B'|1, N] int32 or None) maps this level's positions to rows of `table`."""
+    ([B'|1, N] int32 or None) maps this level's positions to rows of `table`; `ln` = (weight, bias, eps)
+    applies the block's LayerNorm to the rows as they are read."""
     B = table.shape[0]
-    a, b = ops.normalize_split(table, rowmap, split)            # merge.py:84-85
+    a, b = ops.normalize_split(table, rowmap, split, ln)        # merge.py:84-85
     Ns, Nd = a.shape[1], b.shape[1]
     r = ops.merge_count(Ns, ratio)                              # merge.py:90
     keys = ops.sim_argmax(a, b, align_batch)                    # merge.py:87,93-97,112

@@ -56,8 +56,20 @@ def merge_count(num_src: int, ratio: float) -> int:
     return int(_lib.load().vtm_merge_count(num_src, float(ratio)))
 
 
-def normalize_split(x: torch.Tensor, rowmap: Optional[torch.Tensor], split: VtmSplit):
-    """K0.  x [B, N0, C] fp16; rowmap [B'|1, N] int32 or None.  Returns (a [B,Ns,C], b [B,Nd,C])."""
+def _ln_args(ln):
+    """ln = None or (weight [C] fp16, bias [C] fp16 | None, eps)."""
+    if ln is None:
+        return None, None, 0.0
+    w, b, eps = ln
+    _require(w, torch.float16, "ln weight")
+    if b is not None:
+        _require(b, torch.float16, "ln bias")
+    return w.data_ptr(), _ptr(b), float(eps)
+
+
+def normalize_split(x: torch.Tensor, rowmap: Optional[torch.Tensor], split: VtmSplit, ln=None):
+    """K0.  x [B, N0, C] fp16; rowmap [B'|1, N] int32 or None; ln = (weight, bias, eps) fuses the block's
+    LayerNorm in front.  Returns (a [B,Ns,C], b [B,Nd,C])."""
     _require(x, torch.float16, "x")
     B, _, Cc = x.shape
     ns, nd = split_counts(split)
@@ -67,9 +79,10 @@ def normalize_split(x: torch.Tensor, rowmap: Optional[torch.Tensor], split: VtmS
     if rowmap is not None:
         _require(rowmap, torch.int32, "rowmap")
         map_bs = 0 if rowmap.shape[0] == 1 else rowmap.shape[1]
-    check(_lib.load().vtm_normalize_split(x.data_ptr(), x.stride(0), _ptr(rowmap), map_bs, C.byref(split),
-                                          B, Cc, a.data_ptr(), b.data_ptr(), _stream()),
-          "vtm_normalize_split")
+    lw, lb, eps = _ln_args(ln)
+    check(_lib.load().vtm_normalize_split_ln(x.data_ptr(), x.stride(0), _ptr(rowmap), map_bs, C.byref(split),
+                                             B, Cc, lw, lb, eps, a.data_ptr(), b.data_ptr(), _stream()),
+          "vtm_normalize_split_ln")
     STATS.launches += 1
     return a, b
 
@@ -147,8 +160,8 @@ def decode_match(keys: torch.Tensor, edge: torch.Tensor, Nd: int, r: int, want_n
 
 
 def gather_rows(x: torch.Tensor, row_map: Optional[torch.Tensor], L: Optional[int] = None,
-                out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """KC.  y[b, i] = x[b, map[b, i]].  x [B, N, C]; map [B'|1, L] int32."""
+                out: Optional[torch.Tensor] = None, ln=None) -> torch.Tensor:
+    """KC.  y[b, i] = [LayerNorm](x[b, map[b, i]]).  x [B, N, C]; map [B'|1, L] int32."""
     _require(x, torch.float16, "x")
     B, _, Cc = x.shape
     map_bs = 0
@@ -158,8 +171,9 @@ def gather_rows(x: torch.Tensor, row_map: Optional[torch.Tensor], L: Optional[in
         map_bs = 0 if row_map.shape[0] == 1 else L
     if out is None:
         out = torch.empty((B, L, Cc), dtype=torch.float16, device=x.device)
-    check(_lib.load().vtm_gather_rows(x.data_ptr(), x.stride(0), _ptr(row_map), map_bs, B, L, Cc,
-                                      out.data_ptr(), out.stride(0), _stream()), "vtm_gather_rows")
+    lw, lb, eps = _ln_args(ln)
+    check(_lib.load().vtm_gather_rows_ln(x.data_ptr(), x.stride(0), _ptr(row_map), map_bs, B, L, Cc, lw, lb, eps,
+                                         out.data_ptr(), out.stride(0), _stream()), "vtm_gather_rows_ln")
     STATS.launches += 1
     return out
 

@@ -49,9 +49,24 @@ class MergePlan:
         return split_frame(out, self.fsize)
 
 
-def build_merge_plan(module: torch.nn.Module, x: torch.Tensor, tome_info: Dict[str, Any]) -> Optional[MergePlan]:
+# Fuse a plain nn.LayerNorm norm1 into the K0 / KC kernels (its output is then never materialised).
+FUSE_LAYERNORM = True
+
+
+def _fusable_layer_norm(norm: torch.nn.Module, x: torch.Tensor):
+    """(weight, bias, eps) if `norm` is a stock affine nn.LayerNorm over the channel dim in fp16, else None."""
+    if not FUSE_LAYERNORM or type(norm) is not torch.nn.LayerNorm or not norm.elementwise_affine:
+        return None
+    if tuple(norm.normalized_shape) != (x.shape[-1],) or norm.weight.dtype != torch.float16 or not norm.weight.is_cuda:
+        return None
+    return (norm.weight.contiguous(), None if norm.bias is None else norm.bias.contiguous(), float(norm.eps))
+
+
+def build_merge_plan(module: torch.nn.Module, x: torch.Tensor, tome_info: Dict[str, Any],
+                     ln=None) -> Optional[MergePlan]:
     """The body of compute_merge (vidtome/patch.py:14-91).  Returns None when the block is not merged
-    (downsample > max_downsample, patch.py:27,86-88)."""
+    (downsample > max_downsample, patch.py:27,86-88).  With `ln = (weight, bias, eps)`, `x` is the RAW
+    hidden state and norm1 is applied inside the kernels that read it (K0, KC)."""
     original_h, original_w = tome_info["size"]
     original_tokens = original_h * original_w
     downsample = int(math.ceil(math.sqrt(original_tokens // x.shape[1])))    # patch.py:15-17
@@ -81,7 +96,7 @@ def build_merge_plan(module: torch.nn.Module, x: torch.Tensor, tome_info: Dict[s
                 0, stride, torch.Size([1]), generator=generator, device=generator.device)))  # merge.py:56-57
             randfs.append(randf)
             split = VtmSplit.local(L, unm, curF, args["target_stride"], randf)
-            m = merge.match_level(table, mu, split, ratio, align)            # patch.py:45-46
+            m = merge.match_level(table, mu, split, ratio, align, ln)        # patch.py:45-46
             mu, pi = ops.compose_maps(split, m.r, m.keys, m.edge, m.rank, mu, pi, 0, N0)
             levels.append(m)
             unm += m.unm_num                                                 # patch.py:47
@@ -93,7 +108,7 @@ def build_merge_plan(module: torch.nn.Module, x: torch.Tensor, tome_info: Dict[s
         pi = mu
     coin = None
     if args["merge_global"]:                                                 # patch.py:59
-        local_tokens = ops.gather_rows(table, mu)                            # merged local tokens [B, L, C]
+        local_tokens = ops.gather_rows(table, mu, ln=ln)                     # merged local tokens [B, L, C]
         g = getattr(module, "global_tokens", None)
         if g is not None:                                                    # patch.py:60
             coin = float(draw_scalar(generator, lambda: torch.rand(
@@ -126,7 +141,7 @@ def build_merge_plan(module: torch.nn.Module, x: torch.Tensor, tome_info: Dict[s
             merged_tokens = local_tokens
             module.global_tokens = local_tokens.detach().clone()            # patch.py:82
     else:
-        merged_tokens = ops.gather_rows(table, mu)                           # patch.py:50,56 composed
+        merged_tokens = ops.gather_rows(table, mu, ln=ln)                    # patch.py:50,56 composed
     return MergePlan(fsize=fsize, N0=N0, merged_tokens=merged_tokens, pi=pi, levels=levels, randf=randfs,
                      coin=coin)
 
@@ -181,15 +196,21 @@ def make_diffusers_tome_block(block_class: Type[torch.nn.Module]) -> Type[torch.
         def forward(self, hidden_states, attention_mask=None, encoder_hidden_states=None,
                     encoder_attention_mask=None, timestep=None, cross_attention_kwargs=None,
                     class_labels=None) -> torch.Tensor:
+            plan = None
             if self.use_ada_layer_norm:                                       # patch.py:139-146
                 norm_hidden_states = self.norm1(hidden_states, timestep)
             elif self.use_ada_layer_norm_zero:
                 norm_hidden_states, gate_msa, shift_mlp, scale_mlp, gate_mlp = self.norm1(
                     hidden_states, timestep, class_labels, hidden_dtype=hidden_states.dtype)
             else:
-                norm_hidden_states = self.norm1(hidden_states)
+                ln = _fusable_layer_norm(self.norm1, hidden_states) if hidden_states.is_cuda else None
+                if ln is not None:
+                    # norm1 fused into the merge kernels: only the kept rows are ever normalised
+                    plan = build_merge_plan(self, hidden_states, self._tome_info, ln=ln)
+                norm_hidden_states = None if plan is not None else self.norm1(hidden_states)
 
-            plan = build_merge_plan(self, norm_hidden_states, self._tome_info)  # patch.py:149-150
+            if plan is None:
+                plan = build_merge_plan(self, norm_hidden_states, self._tome_info)  # patch.py:149-150
             if plan is not None:
                 norm_hidden_states = plan.merged_tokens
 
