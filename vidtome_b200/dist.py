@@ -59,8 +59,9 @@ def all_gather_tokens(local: torch.Tensor, group=None) -> List[torch.Tensor]:
     all_lens = [int(t.item()) for t in all_lens]
     Lmax = max(all_lens)
     padded = local if L == Lmax else torch.cat([local, local.new_zeros((B, Lmax - L, C))], dim=1)
-    out = torch.empty((w, B, Lmax, C), dtype=local.dtype, device=local.device)
+    out = torch.empty((w * B, Lmax, C), dtype=local.dtype, device=local.device)   # rank-major concatenation
     dist.all_gather_into_tensor(out, padded.contiguous(), group=group)
+    out = out.view(w, B, Lmax, C)
     return [out[k, :, : all_lens[k]] for k in range(w)]
 
 
