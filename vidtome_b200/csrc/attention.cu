@@ -4,20 +4,23 @@
 // Reference: `self.attn1(merged_tokens)` at vidtome/patch.py:157-162 = diffusers Attention; the math is
 // restated in the reference at utils/pnp_utils.py:47-95: softmax(q k^T * scale) v per head.
 //
-// Flash-attention kernel, one CTA per (128-row query tile, head, sample), 192 threads, TWO CTAs per SM
-// (256 TMEM columns and <= 104 KB of shared memory each) so that one CTA's softmax overlaps the other's MMAs:
-//   warp 0      TMA producer: Q tile once, then K/V tiles of BKV keys through a 2-deep ring.  Q, K and V are
-//               read straight out of the [B*L, 3C] projection output through rank-4 tensor maps
-//               (head_dim, token, head, sample); columns beyond head_dim are zero-filled by TMA.
-//   warp 1      MMA issuer (one lane): S_j = Q K_j^T (A, B from shared memory, K-major; only ceil(d/16) K steps),
-//               then O += P_j V_j with A = P_j read from TENSOR MEMORY and B = V_j read MN-major from shared
-//               memory (no transposed copy of V), plus l += P_j 1 against a constant ones tile, so the softmax
-//               denominator is accumulated by the tensor core from the same fp16 P that weights V.
-//   warps 2..5  softmax: one query row per thread.  Pass 1 row max; the reference max only moves when the row
-//               max exceeds it by more than 2^8 (then O and l are rescaled in TMEM); pass 2 writes
-//               P = exp2(s*scale*log2e - m) as fp16 over the consumed score columns using ex2.approx.f16x2
-//               (two exponentials per MUFU op).  TMEM loads are software pipelined.  Finally O / l -> fp16.
-// TMEM (256 columns): S/P [0, BKV) | O [128, 128 + 16*KSTEPS) | l [128 + 16*KSTEPS, +16).
+// Flash-attention kernel, one CTA per (128-row query tile, head, sample), 192 threads, two CTAs per SM
+// (256 TMEM columns, <= 97 KB of shared memory each):
+//   warp 0      TMA producer: Q tile once, then K/V tiles of 64 keys through a ring.  Q, K and V are read straight
+//               out of the [B*L, 3C] projection output through rank-4 tensor maps (head_dim, token, head, sample);
+//               columns beyond head_dim are zero-filled by TMA.
+//   warp 1      MMA issuer: S_j = Q K_j^T (A, B from shared memory, K-major; only ceil(d/16) K steps) into one of
+//               TWO score buffers, and O += P_j V_j with A = P_j read from TENSOR MEMORY and B = V_j read MN-major
+//               from shared memory (no transposed copy of V).  S_{j+1} is issued before P_j is awaited, so the
+//               softmax warps never wait for the QK round trip.  The warp stays converged (elect.sync) so that
+//               descriptor arithmetic runs on the uniform datapath: with head_dim 40 the MMAs are tiny and the
+//               issue rate of this warp matters.
+//   warps 2..5  softmax: one query row per thread; the row's 64 scores are read from TMEM ONCE into registers
+//               (row max -> lazy reference max -> P = exp2(s*scale*log2e - m) as fp16 written over the consumed
+//               score columns, fp32 row sum).  The reference max moves only when exceeded by 2^8; then O is
+//               rescaled in TMEM (after P_{j-1} V_{j-1} has retired).  Finally O / l -> fp16.
+// For head_dim 40 the kernel is bound by the exponential (MUFU.EX2, 16/clk/SM), not by the tensor pipe.
+// TMEM (256 columns): S0/P0 [0,64) | S1/P1 [64,128) | O [128, 128 + 16*KSTEPS).
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -41,80 +44,54 @@ template <int KSTEPS>
 struct FaCfg {
   static constexpr int ATOMS = (KSTEPS + 3) / 4;              // 64-wide head_dim blocks
   static constexpr int DV_N = 16 * KSTEPS;                    // UMMA N of P*V (head_dim rounded up to 16)
-  static constexpr int BKV = ATOMS == 1 ? 128 : 64;           // keys per tile
-  static constexpr int STAGES = 2;
+  static constexpr int BKV = 64;                              // keys per tile (one softmax row = 64 registers)
+  static constexpr int STAGES = ATOMS == 1 ? 4 : 2;           // K/V ring depth
+  static constexpr int MIN_CTAS = 2;                          // co-resident CTAs per SM
   static constexpr uint32_t Q_BYTES = ATOMS * BQ * 128;       // Q tile: ATOMS x [128 rows x 128 B]
   static constexpr uint32_t KV_ATOM = BKV * 128;              // one 64-wide block of a K or V tile
   static constexpr uint32_t TILE_BYTES = ATOMS * KV_ATOM;
   static constexpr uint32_t STAGE_BYTES = 2 * TILE_BYTES;     // K + V
-  static constexpr uint32_t ONES_BYTES = BKV * 128;
-  static constexpr uint32_t O_COL = 128;
-  static constexpr uint32_t L_COL = 128 + DV_N;
-  static constexpr uint32_t TMEM_COLS = (128 + DV_N + 16) <= 256 ? 256 : 512;
-  static constexpr size_t SMEM_BYTES = 1024 + Q_BYTES + ONES_BYTES + static_cast<size_t>(STAGES) * STAGE_BYTES + 128;
+  static constexpr uint32_t O_COL = 2 * BKV;
+  static constexpr uint32_t TMEM_COLS = 256;                  // 2 x 64 score columns + up to 128 O columns
+  static constexpr size_t SMEM_BYTES = 1024 + Q_BYTES + static_cast<size_t>(STAGES) * STAGE_BYTES + 256;
 };
 
-// Row maximum of this thread's BKV scores (TMEM loads pipelined two deep).  TAIL: only the first n_valid exist.
-template <int BKV, bool TAIL>
-__device__ __forceinline__ float fa_row_max(uint32_t s_addr, int n_valid) {
-  float mx = -INFINITY;
-  uint32_t ra[32], rb[32];
-  tmem_ld_32x32b_x32(s_addr, ra);
+// One softmax step on this thread's row of 64 scores, reading S from TMEM exactly once (TMEM read
+// bandwidth, ~64 B/clk/SM, is the scarce resource here: a second pass over S would double it).
+//   r0/r1 hold columns [0,32) / [32,64).  Returns the row maximum.
+template <bool TAIL>
+__device__ __forceinline__ float fa_row_max64(const uint32_t (&r0)[32], const uint32_t (&r1)[32], int n_valid) {
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;   // four chains: latency, not count
 #pragma unroll
-  for (int cb = 0; cb < BKV; cb += 64) {
-    tmem_ld_wait();
-    tmem_ld_32x32b_x32(s_addr + cb + 32, rb);
-#pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (!TAIL || cb + i < n_valid) mx = fmaxf(mx, __uint_as_float(ra[i]));
-    tmem_ld_wait();
-    if (cb + 64 < BKV) tmem_ld_32x32b_x32(s_addr + cb + 64, ra);
-#pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (!TAIL || cb + 32 + i < n_valid) mx = fmaxf(mx, __uint_as_float(rb[i]));
+  for (int i = 0; i < 32; i += 2) {
+    if (!TAIL || i < n_valid) m0 = fmaxf(m0, __uint_as_float(r0[i]));
+    if (!TAIL || i + 1 < n_valid) m1 = fmaxf(m1, __uint_as_float(r0[i + 1]));
+    if (!TAIL || 32 + i < n_valid) m2 = fmaxf(m2, __uint_as_float(r1[i]));
+    if (!TAIL || 33 + i < n_valid) m3 = fmaxf(m3, __uint_as_float(r1[i + 1]));
   }
+  const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
   return mx;
 }
-
-// P = exp2(s*c - mc) as fp16 pairs written over the already consumed score columns (two exps per MUFU op).
-template <int BKV, bool TAIL>
-__device__ __forceinline__ void fa_write_p(uint32_t s_addr, float c, float mc, int n_valid) {
-  uint32_t ra[32], rb[32];
-  tmem_ld_32x32b_x32(s_addr, ra);
+// P = exp2(s*c - mc) for 32 scores -> 16 packed fp16 pairs; accumulates the fp32 row sum.
+template <bool TAIL>
+__device__ __forceinline__ void fa_exp32(const uint32_t (&r)[32], uint32_t (&pk)[16], float c, float mc, int col0,
+                                         int n_valid, float& sum0, float& sum1) {
 #pragma unroll
-  for (int cb = 0; cb < BKV; cb += 64) {
-    uint32_t pk[16];
-    tmem_ld_wait();
-    tmem_ld_32x32b_x32(s_addr + cb + 32, rb);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      float x0 = fmaf(__uint_as_float(ra[2 * i]), c, -mc);
-      float x1 = fmaf(__uint_as_float(ra[2 * i + 1]), c, -mc);
-      if (TAIL) {
-        if (cb + 2 * i >= n_valid) x0 = -INFINITY;
-        if (cb + 2 * i + 1 >= n_valid) x1 = -INFINITY;
-      }
-      pk[i] = ex2_approx_f16x2(pack_f16x2(x0, x1));
+  for (int i = 0; i < 16; ++i) {
+    float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * i]), c, -mc));
+    float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), c, -mc));
+    if (TAIL) {
+      if (col0 + 2 * i >= n_valid) p0 = 0.f;
+      if (col0 + 2 * i + 1 >= n_valid) p1 = 0.f;
     }
-    tmem_st_32x32b_x16(s_addr + (cb >> 1), pk);
-    tmem_ld_wait();
-    if (cb + 64 < BKV) tmem_ld_32x32b_x32(s_addr + cb + 64, ra);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      float x0 = fmaf(__uint_as_float(rb[2 * i]), c, -mc);
-      float x1 = fmaf(__uint_as_float(rb[2 * i + 1]), c, -mc);
-      if (TAIL) {
-        if (cb + 32 + 2 * i >= n_valid) x0 = -INFINITY;
-        if (cb + 32 + 2 * i + 1 >= n_valid) x1 = -INFINITY;
-      }
-      pk[i] = ex2_approx_f16x2(pack_f16x2(x0, x1));
-    }
-    tmem_st_32x32b_x16(s_addr + ((cb + 32) >> 1), pk);
+    sum0 += p0;
+    sum1 += p1;
+    pk[i] = pack_f16x2(p0, p1);
   }
 }
 
 template <int KSTEPS>
-__global__ void __launch_bounds__(FA_THREADS, 2)
+__global__ void __launch_bounds__(FA_THREADS, FaCfg<KSTEPS>::MIN_CTAS)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                   const __grid_constant__ CUtensorMap tm_v, const FaParams p) {
   using C = FaCfg<KSTEPS>;
@@ -123,18 +100,17 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = smem_base;
-  const uint32_t sOnes = sQ + C::Q_BYTES;
-  const uint32_t sKV = sOnes + C::ONES_BYTES;
+  const uint32_t sKV = sQ + C::Q_BYTES;
   const uint32_t bar_base = sKV + STAGES * C::STAGE_BYTES;
-  // 8-byte slots: q_full | k_full[S] | v_full[S] | kv_empty[S] | s_full | p_full | o_done | tmem ptr
+  // 8-byte slots: q_full | k_full[S] | v_full[S] | kv_empty[S] | s_full[2] | p_full[2] | o_ready | tmem ptr
   const uint32_t q_full = bar_base;
   auto k_full = [&](int s) { return bar_base + 8u * (1 + s); };
   auto v_full = [&](int s) { return bar_base + 8u * (1 + STAGES + s); };
   auto kv_empty = [&](int s) { return bar_base + 8u * (1 + 2 * STAGES + s); };
-  const uint32_t s_full = bar_base + 8u * (1 + 3 * STAGES);
-  const uint32_t p_full = bar_base + 8u * (2 + 3 * STAGES);
-  const uint32_t o_done = bar_base + 8u * (3 + 3 * STAGES);
-  const uint32_t tmem_ptr_addr = bar_base + 8u * (4 + 3 * STAGES);
+  auto s_full = [&](int i) { return bar_base + 8u * (1 + 3 * STAGES + i); };
+  auto p_full = [&](int i) { return bar_base + 8u * (3 + 3 * STAGES + i); };
+  const uint32_t o_ready = bar_base + 8u * (5 + 3 * STAGES);
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (6 + 3 * STAGES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -153,26 +129,16 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
       mbar_init(v_full(s), 1);
       mbar_init(kv_empty(s), 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 4);  // one arrival per softmax warp
-    mbar_init(o_done, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(s_full(i), 1);
+      mbar_init(p_full(i), 4);  // one arrival per softmax warp
+    }
+    mbar_init(o_ready, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
     tmem_alloc(tmem_ptr_addr, C::TMEM_COLS);
     tmem_relinquish();
-  }
-  if (warp >= 2) {
-    // ones tile: B operand of the row-sum MMA, MN-major, 128-byte swizzled rows; element 0 of row r = 1.0
-    // sits in 16-byte chunk (r % 8) of the row.  Written through the generic proxy, fenced for the MMA below.
-    const int t = threadIdx.x - 64;
-    for (int i = t; i < BKV * 8; i += 128) {
-      const int r = i >> 3, ch = i & 7;
-      const uint32_t v0 = (ch == (r & 7)) ? 0x00003C00u : 0u;
-      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %2, %2};" ::"r"(sOnes + r * 128 + ch * 16), "r"(v0), "r"(0u)
-                   : "memory");
-    }
-    fence_proxy_async_smem();
   }
   tc_fence_before();
   __syncthreads();
@@ -180,119 +146,138 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
   const uint32_t tmem_o = tmem_base + C::O_COL;
-  const uint32_t tmem_l = tmem_base + C::L_COL;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp converged; one elected lane issues) =====================
+    if (elect_one()) {
       mbar_arrive_expect_tx(q_full, C::Q_BYTES);
       for (int a = 0; a < C::ATOMS; ++a) tma_load_4d(sQ + a * (BQ * 128), &tm_q, q_full, a * 64, q0, h, b);
-      for (int j = 0; j < nkv; ++j) {
-        const int s = j % STAGES;
-        const uint32_t ph = (j / STAGES) & 1u;
-        mbar_wait(kv_empty(s), ph ^ 1u);
-        const uint32_t sk = sKV + s * C::STAGE_BYTES;
-        const uint32_t sv = sk + C::TILE_BYTES;
+    }
+    for (int j = 0; j < nkv; ++j) {
+      const int s = j % STAGES;
+      const uint32_t ph = (j / STAGES) & 1u;
+      mbar_wait(kv_empty(s), ph ^ 1u);
+      const uint32_t sk = sKV + s * C::STAGE_BYTES;
+      const uint32_t sv = sk + C::TILE_BYTES;
+      if (elect_one()) {
         mbar_arrive_expect_tx(k_full(s), C::TILE_BYTES);
         for (int a = 0; a < C::ATOMS; ++a) tma_load_4d(sk + a * C::KV_ATOM, &tm_k, k_full(s), a * 64, j * BKV, h, b);
         mbar_arrive_expect_tx(v_full(s), C::TILE_BYTES);
         for (int a = 0; a < C::ATOMS; ++a) tma_load_4d(sv + a * C::KV_ATOM, &tm_v, v_full(s), a * 64, j * BKV, h, b);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc_qk = umma_idesc_f16(BQ, BKV);
-      constexpr uint32_t idesc_pv = umma_idesc_f16_bmn(BQ, C::DV_N);
-      constexpr uint32_t idesc_l = umma_idesc_f16_bmn(BQ, 16);
-      auto issue_qk = [&](int j) {
-        const int s = j % STAGES;
-        mbar_wait(k_full(s), (j / STAGES) & 1u);
-        tc_fence_after();
-        const uint32_t sk = sKV + s * C::STAGE_BYTES;
+    // ===================== MMA issuer (whole warp converged; one elected lane issues) =====================
+    constexpr uint32_t idesc_qk = umma_idesc_f16(BQ, BKV);
+    constexpr uint32_t idesc_pv = umma_idesc_f16_bmn(BQ, C::DV_N);
+    auto issue_qk = [&](int j) {
+      const int s = j % STAGES;
+      mbar_wait(k_full(s), (j / STAGES) & 1u);
+      tc_fence_after();
+      const uint32_t sk = sKV + s * C::STAGE_BYTES;
+      const uint32_t d_tmem = tmem_base + (j & 1) * BKV;
+      if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < KSTEPS; ++ks) {
           const uint64_t adesc = umma_desc_sw128_kmajor(sQ + (ks >> 2) * (BQ * 128)) + 2u * (ks & 3);
           const uint64_t bdesc = umma_desc_sw128_kmajor(sk + (ks >> 2) * C::KV_ATOM) + 2u * (ks & 3);
-          umma_f16(tmem_base, adesc, bdesc, idesc_qk, ks != 0 ? 1u : 0u);
+          umma_f16(d_tmem, adesc, bdesc, idesc_qk, ks != 0 ? 1u : 0u);
         }
-        umma_commit(s_full);   // also: every earlier MMA (P_{j-1} V_{j-1}) has retired when this fires
-      };
-      mbar_wait(q_full, 0);
-      issue_qk(0);
-      const uint64_t onesdesc = umma_desc_sw128_mnmajor(sOnes, 0);
-      for (int j = 0; j < nkv; ++j) {
-        const int s = j % STAGES;
-        mbar_wait(p_full, j & 1u);                 // P_j in TMEM, O/l rescaled if needed
-        mbar_wait(v_full(s), (j / STAGES) & 1u);
-        tc_fence_after();
-        const uint32_t sv = sKV + s * C::STAGE_BYTES + C::TILE_BYTES;
+        umma_commit(s_full(j & 1));
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    issue_qk(0);
+    for (int j = 0; j < nkv; ++j) {
+      // Scores of the next tile first: they land in the other buffer, whose previous content (P_{j-1}) was
+      // consumed by the P_{j-1} V_{j-1} MMAs issued before (tcgen05.mma executes in issue order).
+      if (j + 1 < nkv) issue_qk(j + 1);
+      const int s = j % STAGES;
+      mbar_wait(v_full(s), (j / STAGES) & 1u);
+      mbar_wait(p_full(j & 1), (j >> 1) & 1u);   // P_j in TMEM, O rescaled if needed
+      tc_fence_after();
+      const uint32_t sv = sKV + s * C::STAGE_BYTES + C::TILE_BYTES;
+      const uint32_t p_tmem = tmem_base + (j & 1) * BKV;
+      if (elect_one()) {
         const uint64_t vdesc = umma_desc_sw128_mnmajor(sv, C::KV_ATOM);
+        if (j == 0) {
 #pragma unroll
-        for (int t = 0; t < BKV / 16; ++t) {
-          const uint32_t acc = (j | t) != 0 ? 1u : 0u;
-          umma_f16_ts(tmem_o, tmem_base + 8u * t, vdesc + 128u * t /* 16 rows x 128 B */, idesc_pv, acc);
-          umma_f16_ts(tmem_l, tmem_base + 8u * t, onesdesc + 128u * t, idesc_l, acc);
+          for (int t = 0; t < BKV / 16; ++t)
+            umma_f16_ts(tmem_o, p_tmem + 8u * t, vdesc + 128u * t, idesc_pv, t != 0 ? 1u : 0u);
+        } else {
+#pragma unroll
+          for (int t = 0; t < BKV / 16; ++t)
+            umma_f16_ts(tmem_o, p_tmem + 8u * t, vdesc + 128u * t /* 16 rows x 128 B */, idesc_pv, 1u);
         }
         umma_commit(kv_empty(s));
-        // S_{j+1} overwrites the columns P_j lives in: tcgen05.mma executes in issue order, so it cannot
-        // pass the P_j V_j products issued just above.
-        if (j + 1 < nkv) issue_qk(j + 1);
-        else umma_commit(o_done);
+        umma_commit(o_ready);
       }
+      __syncwarp();
     }
   } else {
     // ===================== softmax / correction / epilogue =====================
     const int quad = warp & 3;
     const int row = q0 + quad * 32 + lane;
     const uint32_t lane_field = static_cast<uint32_t>(quad * 32) << 16;
-    const uint32_t s_addr = tmem_base + lane_field;
     const float c = p.scale_log2;
     float m_ref = -INFINITY;   // reference max (raw score units) used by the exponentials
+    float l_run = 0.f;         // running denominator (same reference)
     for (int j = 0; j < nkv; ++j) {
-      mbar_wait(s_full, j & 1u);
+      mbar_wait(s_full(j & 1), (j >> 1) & 1u);
       tc_fence_after();
+      const uint32_t s_addr = tmem_base + lane_field + (j & 1) * BKV;
       const int n_valid = p.L - j * BKV;  // keys of this tile that exist
       const bool tail = n_valid < BKV;
-      // ---- pass 1: row maximum
-      const float mx = tail ? fa_row_max<BKV, true>(s_addr, n_valid) : fa_row_max<BKV, false>(s_addr, n_valid);
-      // ---- reference max moves only when exceeded by 2^RESCALE_LOG2 (P stays <= 256, exact after O/l rescale)
+      // ---- the row's 64 scores, read from TMEM once
+      uint32_t r0[32], r1[32];
+      tmem_ld_32x32b_x32(s_addr, r0);
+      tmem_ld_32x32b_x32(s_addr + 32, r1);
+      tmem_ld_wait();
+      const float mx = tail ? fa_row_max64<true>(r0, r1, n_valid) : fa_row_max64<false>(r0, r1, n_valid);
+      // ---- reference max moves only when exceeded by 2^RESCALE_LOG2 (P stays <= 256, exact after the O / l rescale)
       float alpha = 1.f;
       if ((mx - m_ref) * c > RESCALE_LOG2) {
         alpha = ex2_approx((m_ref - mx) * c);     // 0 on the first tile (m_ref = -inf)
         m_ref = mx;
       }
       const float mc = m_ref * c;
-      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
-        // P_{j-1} V_{j-1} has retired (s_full of tile j was committed after it): rescale O and l in place
+      // ---- P over the consumed score columns
+      float sum0 = 0.f, sum1 = 0.f;
+      uint32_t pk[16];
+      if (tail) fa_exp32<true>(r0, pk, c, mc, 0, n_valid, sum0, sum1);
+      else fa_exp32<false>(r0, pk, c, mc, 0, n_valid, sum0, sum1);
+      tmem_st_32x32b_x16(s_addr, pk);
+      if (tail) fa_exp32<true>(r1, pk, c, mc, 32, n_valid, sum0, sum1);
+      else fa_exp32<false>(r1, pk, c, mc, 32, n_valid, sum0, sum1);
+      tmem_st_32x32b_x16(s_addr + 16, pk);
+      l_run = l_run * alpha + (sum0 + sum1);
+      // ---- O rescale: only after P_{j-1} V_{j-1} has retired, and only when a reference max moved
+      if (j > 0) {
+        mbar_wait(o_ready, (j - 1) & 1u);
+        if (__any_sync(0xffffffffu, alpha != 1.f)) {
+          tc_fence_after();
 #pragma unroll
-        for (int cb = 0; cb < C::DV_N + 16; cb += 16) {
-          uint32_t r[16];
-          tmem_ld_32x32b_x16(tmem_o + lane_field + cb, r);
-          tmem_ld_wait();
+          for (int cb = 0; cb < C::DV_N; cb += 16) {
+            uint32_t r[16];
+            tmem_ld_32x32b_x16(tmem_o + lane_field + cb, r);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-          tmem_st_32x32b_x16(tmem_o + lane_field + cb, r);
+            for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+            tmem_st_32x32b_x16(tmem_o + lane_field + cb, r);
+          }
         }
       }
-      // ---- pass 2: P over the consumed score columns
-      if (tail) fa_write_p<BKV, true>(s_addr, c, mc, n_valid);
-      else fa_write_p<BKV, false>(s_addr, c, mc, n_valid);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
+      if (lane == 0) mbar_arrive(p_full(j & 1));
     }
     // ---- epilogue: O / l -> fp16 -> o[b, row, h*d : h*d + d]
-    mbar_wait(o_done, 0);
+    mbar_wait(o_ready, (nkv - 1) & 1u);
     tc_fence_after();
-    float inv;
-    {
-      uint32_t r[16];
-      tmem_ld_32x32b_x16(tmem_l + lane_field, r);
-      tmem_ld_wait();
-      inv = 1.f / __uint_as_float(r[0]);
-    }
+    const float inv = 1.f / l_run;
     __half* orow = p.o + (static_cast<size_t>(b) * p.L + row) * p.C + h * p.d;
 #pragma unroll
     for (int cb = 0; cb < C::DV_N; cb += 16) {

@@ -20,6 +20,18 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   return t;
 }
 
+// One elected lane of a fully converged warp (the warp stays converged, so address/descriptor arithmetic
+// around single-thread instructions can live on the uniform datapath).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
