@@ -199,10 +199,119 @@ decode_match_kernel(const unsigned long long* __restrict__ keys, const int* __re
   }
 }
 
+// ---------------------------------------------------------------- fused single-launch sort
+// Same algorithm in ONE cooperative launch: every CTA keeps its 1024-element tile for both passes, the
+// per-(digit, tile) histogram table is exchanged through global memory and each CTA scans the part of it it
+// needs; phases are separated by a grid-wide barrier (monotonic counter, co-residency guaranteed by
+// cudaLaunchCooperativeKernel).  Used when tiles * Bp CTAs fit on the device at once.
+__device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    } while (v < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// exclusive prefix of hist[bucket][tile] in (bucket, tile) order for ONE (bucket, tile) pair per thread:
+// thread t (t < 256) gets the base of bucket t for this CTA's tile.
+__device__ __forceinline__ uint32_t bucket_base(const uint32_t* __restrict__ h /* [256][tiles] */, int tiles,
+                                                int my_tile, uint32_t* s_scan /* [256] */) {
+  uint32_t total = 0, before = 0;
+  if (threadIdx.x < 256) {
+    const uint32_t* row = h + static_cast<size_t>(threadIdx.x) * tiles;
+    for (int t = 0; t < tiles; ++t) {
+      const uint32_t c = __ldcg(row + t);
+      if (t < my_tile) before += c;
+      total += c;
+    }
+    s_scan[threadIdx.x] = total;
+  }
+  __syncthreads();
+  // inclusive scan over the 256 bucket totals (8 warps of 32)
+  uint32_t incl = 0;
+  if (threadIdx.x < 256) {
+    incl = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((threadIdx.x & 31) >= o) incl += v;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 256 && (threadIdx.x & 31) == 31) s_scan[threadIdx.x >> 5] = incl;   // warp totals
+  __syncthreads();
+  uint32_t base = 0;
+  if (threadIdx.x < 256) {
+    uint32_t warp_off = 0;
+    for (int w = 0; w < (threadIdx.x >> 5); ++w) warp_off += s_scan[w];
+    base = warp_off + incl - total + before;
+  }
+  __syncthreads();
+  return base;
+}
+
+__global__ void __launch_bounds__(TILE)
+radix_sort_fused_kernel(const unsigned long long* __restrict__ keys, int Ns, int tiles, uint32_t* hist0,
+                        uint32_t* hist1, uint16_t* k_tmp, int* id_tmp, int* __restrict__ edge,
+                        int* __restrict__ rank_out, unsigned int* barrier_ctr) {
+  __shared__ uint32_t s_cnt[NW][256];
+  __shared__ uint32_t s_tot[256];
+  __shared__ uint32_t s_base[256];
+  __shared__ uint32_t s_scan[256];
+  const int b = blockIdx.y, tile = blockIdx.x;
+  const unsigned int nblk = gridDim.x * gridDim.y;
+  const size_t row0 = static_cast<size_t>(b) * Ns;
+  const int e = tile * TILE + threadIdx.x;
+  const bool valid = e < Ns;
+  // ---- pass 0 (low byte)
+  uint32_t k16 = valid ? static_cast<uint32_t>(keys[row0 + e] >> 32) & 0xFFFFu : 0u;
+  int bucket = digit_of(k16, 0);
+  int r = tile_rank(bucket, valid, s_cnt, s_tot);
+  uint32_t* h0 = hist0 + static_cast<size_t>(b) * 256 * tiles;
+  if (threadIdx.x < 256) h0[static_cast<size_t>(threadIdx.x) * tiles + tile] = s_tot[threadIdx.x];
+  grid_barrier(barrier_ctr, nblk);
+  uint32_t base = bucket_base(h0, tiles, tile, s_scan);
+  if (threadIdx.x < 256) s_base[threadIdx.x] = base;
+  __syncthreads();
+  if (valid) {
+    const uint32_t pos = s_base[bucket] + r;
+    k_tmp[row0 + pos] = static_cast<uint16_t>(k16);
+    id_tmp[row0 + pos] = e;
+  }
+  grid_barrier(barrier_ctr, 2 * nblk);
+  // ---- pass 1 (high byte) on the pass-0 order
+  int id = e;
+  if (valid) {
+    k16 = __ldcg(k_tmp + row0 + e);
+    id = __ldcg(id_tmp + row0 + e);
+  }
+  bucket = digit_of(k16, 1);
+  r = tile_rank(bucket, valid, s_cnt, s_tot);
+  uint32_t* h1 = hist1 + static_cast<size_t>(b) * 256 * tiles;
+  if (threadIdx.x < 256) h1[static_cast<size_t>(threadIdx.x) * tiles + tile] = s_tot[threadIdx.x];
+  grid_barrier(barrier_ctr, 3 * nblk);
+  base = bucket_base(h1, tiles, tile, s_scan);
+  if (threadIdx.x < 256) s_base[threadIdx.x] = base;
+  __syncthreads();
+  if (valid) {
+    const uint32_t pos = s_base[bucket] + r;
+    edge[row0 + pos] = id;
+    rank_out[row0 + id] = static_cast<int>(pos);
+  }
+}
+
 struct SortWs {
   uint32_t* hist;
+  uint32_t* hist1;
   uint16_t* k_tmp;
   int* id_tmp;
+  unsigned int* barrier;
 };
 size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
 size_t sort_ws_layout(int Bp, int Ns, void* base, SortWs* ws) {
@@ -211,6 +320,10 @@ size_t sort_ws_layout(int Bp, int Ns, void* base, SortWs* ws) {
   uint8_t* p = static_cast<uint8_t*>(base);
   if (ws) ws->hist = reinterpret_cast<uint32_t*>(p + off);
   off += align256(sizeof(uint32_t) * static_cast<size_t>(Bp) * 256 * tiles);
+  if (ws) ws->hist1 = reinterpret_cast<uint32_t*>(p + off);
+  off += align256(sizeof(uint32_t) * static_cast<size_t>(Bp) * 256 * tiles);
+  if (ws) ws->barrier = reinterpret_cast<unsigned int*>(p + off);
+  off += 256;
   if (ws) ws->k_tmp = reinterpret_cast<uint16_t*>(p + off);
   off += align256(sizeof(uint16_t) * static_cast<size_t>(Bp) * Ns);
   if (ws) ws->id_tmp = reinterpret_cast<int*>(p + off);
@@ -237,6 +350,23 @@ extern "C" int vtm_topr_sort(const uint64_t* keys_dev, int32_t Bp, int32_t Ns, i
   const int tiles = (Ns + TILE - 1) / TILE;
   const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(keys_dev);
   dim3 grid(tiles, Bp);
+  // single cooperative launch when every CTA can be resident at once
+  {
+    int dev = 0, sms = 0, per_sm = 0, coop = 0;
+    int rc = cuda_rc(cudaGetDevice(&dev));
+    if (rc) return rc;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, radix_sort_fused_kernel, TILE, 0);
+    if (coop && static_cast<long long>(tiles) * Bp <= static_cast<long long>(sms) * per_sm) {
+      rc = cuda_rc(cudaMemsetAsync(ws.barrier, 0, sizeof(unsigned int), st));
+      if (rc) return rc;
+      int ns = Ns, tl = tiles;
+      void* args[] = {(void*)&keys, (void*)&ns, (void*)&tl, (void*)&ws.hist, (void*)&ws.hist1, (void*)&ws.k_tmp,
+                      (void*)&ws.id_tmp, (void*)&edge_dev, (void*)&rank_dev, (void*)&ws.barrier};
+      return cuda_rc(cudaLaunchCooperativeKernel((const void*)radix_sort_fused_kernel, grid, dim3(TILE), args, 0, st));
+    }
+  }
   radix_hist_kernel<0><<<grid, TILE, 0, st>>>(keys, nullptr, Ns, tiles, ws.hist);
   radix_scan_kernel<<<Bp, 1024, 0, st>>>(ws.hist, tiles);
   radix_scatter_kernel<0><<<grid, TILE, 0, st>>>(keys, nullptr, nullptr, Ns, tiles, ws.hist, ws.k_tmp,

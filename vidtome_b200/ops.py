@@ -120,7 +120,8 @@ def topr_sort(keys: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     rank = torch.empty((Bp, Ns), dtype=torch.int32, device=keys.device)
     check(lib.vtm_topr_sort(keys.data_ptr(), Bp, Ns, edge.data_ptr(), rank.data_ptr(), ws.data_ptr(),
                             ws_bytes, _stream()), "vtm_topr_sort")
-    STATS.launches += 6
+    # one cooperative launch when all (tiles x Bp) CTAs are co-resident (2 per SM), else 6 small launches
+    STATS.launches += 1 if ((Ns + 1023) // 1024) * Bp <= 2 * torch.cuda.get_device_properties(keys.device).multi_processor_count else 6
     return edge, rank
 
 
