@@ -52,6 +52,13 @@ class MergePlan:
 # Fuse a plain nn.LayerNorm norm1 into the K0 / KC kernels (its output is then never materialised).
 FUSE_LAYERNORM = True
 
+# How `merge_global=True` obtains the global token set when several ranks each hold one chunk:
+#   "recurrence" — the reference's semantics (patch.py:59-82): whatever the previous chunk processed by THIS
+#                  process left in module.global_tokens;
+#   "allgather"  — chunk-per-GPU variant (option A): one NCCL all-gather of the local merged tokens
+#                  per merged block; rank k matches against the tokens of rank (k-1) mod G (dist.py).
+GLOBAL_EXCHANGE = "recurrence"
+
 
 def _fusable_layer_norm(norm: torch.nn.Module, x: torch.Tensor):
     """(weight, bias, eps) if `norm` is a stock affine nn.LayerNorm over the channel dim in fp16, else None."""
@@ -110,6 +117,12 @@ def build_merge_plan(module: torch.nn.Module, x: torch.Tensor, tome_info: Dict[s
     if args["merge_global"]:                                                 # patch.py:59
         local_tokens = ops.gather_rows(table, mu, ln=ln)                     # merged local tokens [B, L, C]
         g = getattr(module, "global_tokens", None)
+        exchanged = False
+        if GLOBAL_EXCHANGE == "allgather":
+            from . import dist as _dist
+            if _dist.world() > 1:
+                g = _dist.exchange_global_tokens(local_tokens)              # the one collective of this path
+                exchanged = True
         if g is not None:                                                    # patch.py:60
             coin = float(draw_scalar(generator, lambda: torch.rand(
                 1, generator=generator, device=generator.device)))                            # patch.py:62
@@ -132,7 +145,8 @@ def build_merge_plan(module: torch.nn.Module, x: torch.Tensor, tome_info: Dict[s
             # patch.py:80: global_tokens <- u(merged_tokens), the local partition after unmerging;
             # kept on the device instead of .cpu()
             tau_local = tau[:, off:off + L].contiguous()
-            module.global_tokens = ops.unmerge_add(merged_tokens, tau_local, None)
+            if not exchanged:
+                module.global_tokens = ops.unmerge_add(merged_tokens, tau_local, None)
             # compose with the local unmerge: pi_total[p] = tau[off + pi[p]]
             if pi.shape[0] != tau.shape[0]:
                 pi = pi.expand(tau.shape[0], -1)
