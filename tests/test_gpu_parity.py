@@ -281,3 +281,52 @@ def test_fused_layernorm_block_equals_unfused_block():
             patch.FUSE_LAYERNORM = True
     err = (outs[0] - outs[1]).abs()
     assert (err <= 2e-2 * outs[1].abs().max()).float().mean() > 0.98
+
+
+def test_single_frame_and_degenerate_ratios(monkeypatch):
+    """Edge cases of the operator API against the oracle: F = 1 (no src tokens at all), a ratio so small that
+    r = 0, and ratio >= 1 (every src token merged)."""
+    from vidtome_b200 import merge
+    rng = np.random.default_rng(5)
+    x = _exact_video_fast(rng, 2, 4, 40, 128)
+    xt = torch.from_numpy(x).cuda()
+    # F = 1 with carried tokens: merged = dst order (frame tokens, then the unm_pre carried ones), unmerge = identity
+    Replay(monkeypatch, randint=[0])
+    m, u, ret = merge.bipartite_soft_matching_randframe(xt, 1, 0.9, 17, cuda_gen())
+    om = O.bipartite_soft_matching_randframe(x, 1, 0.9, 17, 0)
+    assert ret["unm_num"] == om.unm_num == 0
+    np.testing.assert_array_equal(m(xt).cpu().numpy(), om.merge(x))
+    np.testing.assert_array_equal(u(m(xt)).cpu().numpy(), x)
+    # r = 0 and r = Ns
+    for ratio, rf in ((1e-6, 1), (1.0, 2), (3.0, 3)):
+        Replay(monkeypatch, randint=[rf])
+        m, u, ret = merge.bipartite_soft_matching_randframe(xt, 4, ratio, 0, cuda_gen())
+        om = O.bipartite_soft_matching_randframe(x, 4, ratio, 0, rf)
+        assert ret["unm_num"] == om.unm_num
+        np.testing.assert_array_equal(m(xt).cpu().numpy(), om.merge(x))
+        np.testing.assert_array_equal(u(m(xt)).cpu().numpy(), om.unmerge(om.merge(x)))
+
+
+def test_unsupported_head_dim_uses_module_attention():
+    """head_dim 160 (SD1.5 ds4 blocks with max_downsample=4) is outside KD's range: the block must call the
+    module's own attn1 on the merged tokens, as the reference does, and still produce a finite result."""
+    import vidtome_b200
+    from vidtome_b200 import patch
+    from vidtome_b200.skeleton import BasicTransformerBlock, ModelMixin
+
+    class One(ModelMixin):
+        def __init__(self):
+            super().__init__()
+            self.block = BasicTransformerBlock(1280, 8)
+
+        def forward(self, latent, hidden):
+            return self.block(hidden)
+
+    torch.manual_seed(0)
+    net = One().half().cuda().eval()
+    assert not patch._plain_attention_module(net.block.attn1)
+    vidtome_b200.apply_patch(net, batch_size=2)
+    h = torch.randn(8, 64, 1280, device="cuda", dtype=torch.float16)
+    with torch.no_grad():
+        out = net(torch.zeros(8, 4, 8, 8, device="cuda"), h)
+    assert out.shape == h.shape and torch.isfinite(out).all()

@@ -386,7 +386,8 @@ extern "C" int vtm_compose_maps(const vtm_split_t* split, int32_t r, int32_t Ns,
   Split sp;
   int rc = make_split(split, &sp);
   if (rc) return rc;
-  if (!keys_dev || !edge_dev || !rank_dev || !mu_out_dev || !pi_out_dev) return VTM_E_NULL;
+  if (!mu_out_dev || !pi_out_dev) return VTM_E_NULL;
+  if (Ns > 0 && (!keys_dev || !edge_dev || !rank_dev)) return VTM_E_NULL;   // Ns == 0: nothing was matched
   if (sp.Ns != Ns || sp.Nd != Nd || r < 0 || r > Ns || Bp <= 0 || N0 <= 0 || Nd <= 0) return VTM_E_SHAPE;
   if (!pi_in_dev && N0 + pi_offset > sp.N) return VTM_E_SHAPE;
   const int Lnext = (Ns - r) + Nd;

@@ -71,8 +71,14 @@ def match_level(table: torch.Tensor, rowmap: Optional[torch.Tensor], split: VtmS
     ([B'|1, N] int32 or None) maps this level's positions to rows of `table`; `ln` = (weight, bias, eps)
     applies the block's LayerNorm to the rows as they are read."""
     B = table.shape[0]
+    Ns, Nd = ops.split_counts(split)
+    if Ns == 0:
+        # a single frame (stride 1): every token is dst (merge.py:58-69 with an empty a_idx), nothing to match
+        empty64 = torch.empty((1 if align_batch else B, 0), dtype=torch.int64, device=table.device)
+        empty32 = torch.empty((empty64.shape[0], 0), dtype=torch.int32, device=table.device)
+        return LevelMatch(split=split, B=B, Bp=empty64.shape[0], Ns=0, Nd=Nd, r=0, keys=empty64, edge=empty32,
+                          rank=empty32)
     a, b = ops.normalize_split(table, rowmap, split, ln)        # merge.py:84-85
-    Ns, Nd = a.shape[1], b.shape[1]
     r = ops.merge_count(Ns, ratio)                              # merge.py:90
     keys = ops.sim_argmax(a, b, align_batch)                    # merge.py:87,93-97,112
     edge, rank = ops.topr_sort(keys)                            # merge.py:98,113

@@ -137,8 +137,8 @@ def compose_maps(split: VtmSplit, r: int, keys: torch.Tensor, edge: torch.Tensor
         _require(mu_in, torch.int32, "mu_in")
     if pi_in is not None:
         _require(pi_in, torch.int32, "pi_in")
-    check(_lib.load().vtm_compose_maps(C.byref(split), r, Ns, nd, Bp, keys.data_ptr(), edge.data_ptr(),
-                                       rank.data_ptr(), _ptr(mu_in), _ptr(pi_in), pi_offset, N0,
+    kp, ep, rp = (None, None, None) if Ns == 0 else (keys.data_ptr(), edge.data_ptr(), rank.data_ptr())
+    check(_lib.load().vtm_compose_maps(C.byref(split), r, Ns, nd, Bp, kp, ep, rp, _ptr(mu_in), _ptr(pi_in), pi_offset, N0,
                                        mu_out.data_ptr(), pi_out.data_ptr(), _stream()), "vtm_compose_maps")
     STATS.launches += 1
     return mu_out, pi_out
@@ -148,6 +148,10 @@ def decode_match(keys: torch.Tensor, edge: torch.Tensor, Nd: int, r: int, want_n
     """Expand KA/KB1 results to the reference's int64 index tensors: (unm_idx, src_idx, dst_idx[, node_max, node_idx])."""
     Bp, Ns = keys.shape
     dev = keys.device
+    if Ns == 0:
+        e = torch.empty((Bp, 0, 1), dtype=torch.int64, device=dev)
+        extra = (torch.empty((Bp, 0), dtype=torch.float16, device=dev), torch.empty((Bp, 0), dtype=torch.int64, device=dev))
+        return (e, e.clone(), e.clone()) + (extra if want_node else ())
     unm = torch.empty((Bp, Ns - r, 1), dtype=torch.int64, device=dev)
     src = torch.empty((Bp, r, 1), dtype=torch.int64, device=dev)
     dst = torch.empty((Bp, r, 1), dtype=torch.int64, device=dev)

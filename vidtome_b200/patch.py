@@ -189,7 +189,13 @@ def _plain_attention_module(attn: torch.nn.Module) -> bool:
     if any(getattr(attn, n).bias is not None for n in ("to_q", "to_k", "to_v")):
         return False
     to_out = attn.to_out
-    return isinstance(to_out, (torch.nn.ModuleList, torch.nn.Sequential)) and isinstance(to_out[0], torch.nn.Linear)
+    if not (isinstance(to_out, (torch.nn.ModuleList, torch.nn.Sequential)) and isinstance(to_out[0], torch.nn.Linear)):
+        return False
+    C = attn.to_q.weight.shape[1]
+    if attn.to_q.weight.shape[0] != C or attn.to_k.weight.shape != attn.to_q.weight.shape:
+        return False                       # inner dim != query dim or cross-attention shaped K/V
+    head_dim = C // int(attn.heads)
+    return head_dim * int(attn.heads) == C and head_dim % 8 == 0 and head_dim <= 128   # KD's supported range
 
 
 def make_tome_block(block_class: Type[torch.nn.Module]) -> Type[torch.nn.Module]:
