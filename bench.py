@@ -224,7 +224,10 @@ def run_ours(args):
                 "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": round(tf / pk["tf_sust"], 3),
                 "peak_source": pk["src"] + " (sustained cuBLAS bf16: kernel timed inside a long step)",
                 "launches": len(ka), "share_of_step": round(ka_ms / ms, 3),
-                "algorithmic_GB_per_step": round(ka_bytes / args.steps / 1e9, 3), "traffic": None}
+                "algorithmic_GB_per_step": round(ka_bytes / args.steps / 1e9, 3),
+                # dram__bytes_read.sum + dram__bytes_write.sum of the largest KA launch of the step (C2 ds1 level 1:
+                # 84.7 MB algorithmic) from the ncu --set full capture in profiles/r01_ka_ncu_summary.md
+                "traffic": 108.5e6, "traffic_launch": "B=2 Ns=49152 Nd=16384 C=320", "traffic_algorithmic": 84.7e6}
         value = world * args.steps / (ms / 1e3)
         out = {
             "metric": "denoising steps/sec (SD1.5, 16-frame chunk)", "value": round(value, 3), "unit": "steps/s",

@@ -185,24 +185,29 @@ gather_rows_kernel(const __half* __restrict__ x, long long x_bs, const int* __re
     const long long o = o0 + grp;
     const bool live = o < total;
     const __half* src = x;
-    const __half* rs = resid;
     __half* dst = y;
+    int b = 0, i = 0;
     if (live) {
-      const int b = static_cast<int>(o / L);
-      const int i = static_cast<int>(o - static_cast<long long>(b) * L);
-      const int srow = map ? map[b * map_bs + i] : i;
-      src = x + b * x_bs + static_cast<long long>(srow) * C;
+      b = static_cast<int>(o / L);
+      i = static_cast<int>(o - static_cast<long long>(b) * L);
       dst = y + b * y_bs + static_cast<long long>(i) * C;
-      if (ADD) rs = resid + (static_cast<long long>(b) * L + i) * C;
     }
     uint4 v[P], rr[P];
+    // residual rows do not depend on the map: get them in flight before the (dependent) map lookup
+    if (ADD && live) {
+      const __half* rs = resid + (static_cast<long long>(b) * L + i) * C;
 #pragma unroll
-    for (int i = 0; i < P; ++i) {
-      v[i] = make_uint4(0, 0, 0, 0);
-      if (live && sub + G * i < vecs) {
-        v[i] = ld_nc_16(src + (sub + G * i) * 8);
-        if (ADD) rr[i] = ld_nc_16(rs + (sub + G * i) * 8);
-      }
+      for (int k = 0; k < P; ++k)
+        if (sub + G * k < vecs) rr[k] = ld_nc_16(rs + (sub + G * k) * 8);
+    }
+    if (live) {
+      const int srow = map ? map[b * map_bs + i] : i;
+      src = x + b * x_bs + static_cast<long long>(srow) * C;
+    }
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+      v[k] = make_uint4(0, 0, 0, 0);
+      if (live && sub + G * k < vecs) v[k] = ld_nc_16(src + (sub + G * k) * 8);
     }
     if (!ADD && ln.w) layer_norm_row<G, P>(v, sub, vecs, C, ln);
 #pragma unroll
