@@ -330,3 +330,70 @@ def test_unsupported_head_dim_uses_module_attention():
     with torch.no_grad():
         out = net(torch.zeros(8, 4, 8, 8, device="cuda"), h)
     assert out.shape == h.shape and torch.isfinite(out).all()
+
+
+# --------------------------------------------------------------------------- other BASELINE configs
+def _plan_properties(plan, table):
+    B, N0, C = table.shape
+    L = plan.merged_tokens.shape[1]
+    back = plan.unmerge(plan.merged_tokens).reshape(B, N0, C)
+    pi = plan.pi.long()
+    if pi.shape[0] != B:
+        pi = pi.expand(B, -1)
+    assert torch.equal(back, torch.gather(plan.merged_tokens, 1, pi[..., None].expand(-1, -1, C)))
+    for b in range(B):
+        assert torch.unique(pi[b]).numel() == L
+    return L
+
+
+def test_config4_sd21_768_f8_shapes():
+    """BASELINE config 4 block shapes (SD2.1 768x768: latent 96x96, 8-frame chunks): ds1 T=9216, C=320 and
+    ds2 T=2304, C=640 — level sizes and merged lengths of SURVEY App. B, plus the gather properties."""
+    from types import SimpleNamespace
+    from vidtome_b200 import patch
+    for (T, C, levels, Lwant) in ((9216, 320, [(55296, 18432, 49766), (9216, 14746, 8294)], 15668),
+                                  (2304, 640, [(13824, 4608, 12441), (2304, 3687, 2073)], 3918)):
+        B, F = 2, 8
+        g = torch.Generator(device="cuda").manual_seed(T)
+        base = torch.randn((B, 1, T, C), generator=g, device="cuda")
+        x = (base + 0.1 * torch.randn((B, F, T, C), generator=g, device="cuda")).half().reshape(B * F, T, C)
+        info = {"size": (96, 96), "hooks": [], "args": dict(max_downsample=2, generator=None, seed=123, batch_size=B,
+                align_batch=False, merge_global=False, global_merge_ratio=0.8, local_merge_ratio=0.9,
+                global_rand=0.5, target_stride=4)}
+        plan = patch.build_merge_plan(SimpleNamespace(generator=cuda_gen(), global_tokens=None), x, info)
+        assert [(m.Ns, m.Nd, m.r) for m in plan.levels] == levels
+        assert _plan_properties(plan, x.reshape(B, F * T, C)) == Lwant
+        del plan, x
+        torch.cuda.empty_cache()
+
+
+def test_config3_global_recurrence_through_driver():
+    """BASELINE config 3 flavour: 4-frame chunks with local + global merging through the patched skeleton and the
+    chunked denoising driver (generate.py:205-236): the second chunk of a step sees the first chunk's tokens
+    (merged length grows from L to 2L - r), and update_patch(global_tokens=None) resets every block."""
+    import vidtome_b200
+    from vidtome_b200 import patch
+    from vidtome_b200.driver import ChunkedDenoiser
+    from vidtome_b200.skeleton import make_skeleton
+    net = make_skeleton("tiny", device="cuda", max_downsample=1)
+    vidtome_b200.apply_patch(net, batch_size=2, merge_global=True, local_merge_ratio=0.9, global_merge_ratio=0.8)
+    lengths = []
+    real = patch.build_merge_plan
+
+    def spy(module, x, info, ln=None):
+        plan = real(module, x, info, ln=ln)
+        if plan is not None:
+            lengths.append(plan.merged_tokens.shape[1])
+        return plan
+    patch.build_merge_plan = spy
+    try:
+        den = ChunkedDenoiser(net, n_timesteps=4, chunk_size=4, merge_global=True)
+        x = torch.randn(8, 4, 16, 16, device="cuda", dtype=torch.float16)
+        x1 = den.step(x, 0)
+    finally:
+        patch.build_merge_plan = real
+    assert torch.isfinite(x1).all() and x1.shape == x.shape
+    # two merged blocks (ds1) x two chunks; T=256, F=4: L = 64 + int-truncated rest = 333; second chunk: 2L - int(0.8 L)
+    L = 333
+    assert lengths == [L, L, 2 * L - int(L * 0.8), 2 * L - int(L * 0.8)] or sorted(lengths) == sorted([L, L, 2 * L - int(L * 0.8), 2 * L - int(L * 0.8)])
+    assert all(getattr(b, "global_tokens", None) is None for b in net.blocks)   # reset by post_iter
