@@ -193,3 +193,19 @@ def test_generators_stay_in_lockstep_hooks():
     states = [b.generator.get_state() for b in net.blocks]
     assert all(torch.equal(states[0], s) for s in states[1:])
     assert net._tome_info["size"] == (8, 8)
+
+
+def test_markstein_division_used_by_k0_is_exact():
+    """K0 divides a row by its fp16-rounded norm with q0 = RN(x r), rem = x - q0 n (FMA), q = RN(q0 + rem r),
+    r = RN(1/n).  This equals IEEE x / n for every fp16 numerator and fp16 normal norm (so the kernel keeps
+    torch's `metric / metric.norm()` semantics, merge.py:84, at one division per row)."""
+    x = np.arange(0, 0x7C00, dtype=np.uint16).view(np.float16).astype(np.float32)
+    rng = np.random.default_rng(0)
+    norms = np.unique(rng.integers(0x0400, 0x7BFF, size=600).astype(np.uint16)).view(np.float16).astype(np.float32)
+    for n in norms:
+        n32 = np.float32(n)
+        r = np.float32(1.0) / n32
+        q0 = (x * r).astype(np.float32)
+        rem = (x.astype(np.float64) - q0.astype(np.float64) * np.float64(n32)).astype(np.float32)
+        q = (q0.astype(np.float64) + rem.astype(np.float64) * np.float64(r)).astype(np.float32)
+        assert np.array_equal(q, x / n32)

@@ -6,7 +6,7 @@
 //
 // Flash-attention kernel, one CTA per (128-row query tile, head, sample), 192 threads, two CTAs per SM
 // (256 TMEM columns, <= 97 KB of shared memory each):
-//   warp 0      TMA producer: Q tile once, then K/V tiles of 64 keys through a ring.  Q, K and V are read straight
+//   warp 0      TMA producer: Q tile once, then K/V tiles of BKV keys through a ring.  Q, K and V are read straight
 //               out of the [B*L, 3C] projection output through rank-4 tensor maps (head_dim, token, head, sample);
 //               columns beyond head_dim are zero-filled by TMA.
 //   warp 1      MMA issuer: S_j = Q K_j^T (A, B from shared memory, K-major; only ceil(d/16) K steps) into one of
@@ -20,7 +20,8 @@
 //               score columns, fp32 row sum).  The reference max moves only when exceeded by 2^8; then O is
 //               rescaled in TMEM (after P_{j-1} V_{j-1} has retired).  Finally O / l -> fp16.
 // For head_dim 40 the kernel is bound by the exponential (MUFU.EX2, 16/clk/SM), not by the tensor pipe.
-// TMEM (256 columns): S0/P0 [0,64) | S1/P1 [64,128) | O [128, 128 + 16*KSTEPS).
+// TMEM (256 columns): S0/P0 [0,BKV) | S1/P1 [BKV,2 BKV) | O [2 BKV, 2 BKV + 16*KSTEPS); BKV = 96 keys per tile when
+// that fits (head_dim <= 64), else 64.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -44,8 +45,9 @@ template <int KSTEPS>
 struct FaCfg {
   static constexpr int ATOMS = (KSTEPS + 3) / 4;              // 64-wide head_dim blocks
   static constexpr int DV_N = 16 * KSTEPS;                    // UMMA N of P*V (head_dim rounded up to 16)
-  static constexpr int BKV = 64;                              // keys per tile (one softmax row = 64 registers)
-  static constexpr int STAGES = ATOMS == 1 ? 4 : 2;           // K/V ring depth
+  // keys per tile: the largest multiple of 32 whose two score buffers fit next to O in 256 TMEM columns
+  static constexpr int BKV = (2 * 96 + DV_N) <= 256 ? 96 : 64;
+  static constexpr int STAGES = ATOMS == 1 ? 3 : 2;           // K/V ring depth
   static constexpr int MIN_CTAS = 2;                          // co-resident CTAs per SM
   static constexpr uint32_t Q_BYTES = ATOMS * BQ * 128;       // Q tile: ATOMS x [128 rows x 128 B]
   static constexpr uint32_t KV_ATOM = BKV * 128;              // one 64-wide block of a K or V tile
@@ -56,21 +58,23 @@ struct FaCfg {
   static constexpr size_t SMEM_BYTES = 1024 + Q_BYTES + static_cast<size_t>(STAGES) * STAGE_BYTES + 256;
 };
 
-// One softmax step on this thread's row of 64 scores, reading S from TMEM exactly once (TMEM read
-// bandwidth, ~64 B/clk/SM, is the scarce resource here: a second pass over S would double it).
-//   r0/r1 hold columns [0,32) / [32,64).  Returns the row maximum.
-template <bool TAIL>
-__device__ __forceinline__ float fa_row_max64(const uint32_t (&r0)[32], const uint32_t (&r1)[32], int n_valid) {
-  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;   // four chains: latency, not count
+// Row maximum of this thread's BKV = 32*NCH scores, held in registers (read from TMEM exactly once: TMEM read
+// bandwidth is shared with the MMAs, and a second pass over S would double it).  Four independent chains.
+template <int NCH, bool TAIL>
+__device__ __forceinline__ float fa_row_max(const uint32_t (&r)[NCH][32], int n_valid) {
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-  for (int i = 0; i < 32; i += 2) {
-    if (!TAIL || i < n_valid) m0 = fmaxf(m0, __uint_as_float(r0[i]));
-    if (!TAIL || i + 1 < n_valid) m1 = fmaxf(m1, __uint_as_float(r0[i + 1]));
-    if (!TAIL || 32 + i < n_valid) m2 = fmaxf(m2, __uint_as_float(r1[i]));
-    if (!TAIL || 33 + i < n_valid) m3 = fmaxf(m3, __uint_as_float(r1[i + 1]));
+  for (int ch = 0; ch < NCH; ++ch) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const int col = ch * 32 + i;
+      if (!TAIL || col < n_valid) m0 = fmaxf(m0, __uint_as_float(r[ch][i]));
+      if (!TAIL || col + 1 < n_valid) m1 = fmaxf(m1, __uint_as_float(r[ch][i + 1]));
+      if (!TAIL || col + 2 < n_valid) m2 = fmaxf(m2, __uint_as_float(r[ch][i + 2]));
+      if (!TAIL || col + 3 < n_valid) m3 = fmaxf(m3, __uint_as_float(r[ch][i + 3]));
+    }
   }
-  const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-  return mx;
+  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 }
 // P = exp2(s*c - mc) for 32 scores -> 16 packed fp16 pairs; accumulates the fp32 row sum.
 template <bool TAIL>
@@ -102,15 +106,18 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
   const uint32_t sQ = smem_base;
   const uint32_t sKV = sQ + C::Q_BYTES;
   const uint32_t bar_base = sKV + STAGES * C::STAGE_BYTES;
-  // 8-byte slots: q_full | k_full[S] | v_full[S] | kv_empty[S] | s_full[2] | p_full[2] | o_ready | tmem ptr
+  // 8-byte slots: q_full | k_full[S] | v_full[S] | kv_empty[S] | s_full[2] | p_full[2] | o_ready[2] | tmem ptr
   const uint32_t q_full = bar_base;
   auto k_full = [&](int s) { return bar_base + 8u * (1 + s); };
   auto v_full = [&](int s) { return bar_base + 8u * (1 + STAGES + s); };
   auto kv_empty = [&](int s) { return bar_base + 8u * (1 + 2 * STAGES + s); };
   auto s_full = [&](int i) { return bar_base + 8u * (1 + 3 * STAGES + i); };
   auto p_full = [&](int i) { return bar_base + 8u * (3 + 3 * STAGES + i); };
-  const uint32_t o_ready = bar_base + 8u * (5 + 3 * STAGES);
-  const uint32_t tmem_ptr_addr = bar_base + 8u * (6 + 3 * STAGES);
+  // o_ready[i] completes when P_j V_j (j & 1 == i) has retired.  Two barriers so that a softmax warp may skip the
+  // wait when it has nothing to rescale: the MMA warp is never more than one tile ahead, so the barrier consulted
+  // is at most one completion ahead of the one asked for and the parity test stays unambiguous.
+  auto o_ready = [&](int i) { return bar_base + 8u * (5 + 3 * STAGES + i); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (7 + 3 * STAGES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -133,7 +140,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
       mbar_init(s_full(i), 1);
       mbar_init(p_full(i), 4);  // one arrival per softmax warp
     }
-    mbar_init(o_ready, 1);
+    mbar_init(o_ready(0), 1);
+    mbar_init(o_ready(1), 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -212,7 +220,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             umma_f16_ts(tmem_o, p_tmem + 8u * t, vdesc + 128u * t /* 16 rows x 128 B */, idesc_pv, 1u);
         }
         umma_commit(kv_empty(s));
-        umma_commit(o_ready);
+        umma_commit(o_ready(j & 1));
       }
       __syncwarp();
     }
@@ -230,12 +238,13 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
       const uint32_t s_addr = tmem_base + lane_field + (j & 1) * BKV;
       const int n_valid = p.L - j * BKV;  // keys of this tile that exist
       const bool tail = n_valid < BKV;
-      // ---- the row's 64 scores, read from TMEM once
-      uint32_t r0[32], r1[32];
-      tmem_ld_32x32b_x32(s_addr, r0);
-      tmem_ld_32x32b_x32(s_addr + 32, r1);
+      // ---- the row's scores, read from TMEM once
+      constexpr int NCH = BKV / 32;
+      uint32_t r[NCH][32];
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) tmem_ld_32x32b_x32(s_addr + 32 * ch, r[ch]);
       tmem_ld_wait();
-      const float mx = tail ? fa_row_max64<true>(r0, r1, n_valid) : fa_row_max64<false>(r0, r1, n_valid);
+      const float mx = tail ? fa_row_max<NCH, true>(r, n_valid) : fa_row_max<NCH, false>(r, n_valid);
       // ---- reference max moves only when exceeded by 2^RESCALE_LOG2 (P stays <= 256, exact after the O / l rescale)
       float alpha = 1.f;
       if ((mx - m_ref) * c > RESCALE_LOG2) {
@@ -245,28 +254,26 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
       const float mc = m_ref * c;
       // ---- P over the consumed score columns
       float sum0 = 0.f, sum1 = 0.f;
-      uint32_t pk[16];
-      if (tail) fa_exp32<true>(r0, pk, c, mc, 0, n_valid, sum0, sum1);
-      else fa_exp32<false>(r0, pk, c, mc, 0, n_valid, sum0, sum1);
-      tmem_st_32x32b_x16(s_addr, pk);
-      if (tail) fa_exp32<true>(r1, pk, c, mc, 32, n_valid, sum0, sum1);
-      else fa_exp32<false>(r1, pk, c, mc, 32, n_valid, sum0, sum1);
-      tmem_st_32x32b_x16(s_addr + 16, pk);
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        uint32_t pk[16];
+        if (tail) fa_exp32<true>(r[ch], pk, c, mc, 32 * ch, n_valid, sum0, sum1);
+        else fa_exp32<false>(r[ch], pk, c, mc, 32 * ch, n_valid, sum0, sum1);
+        tmem_st_32x32b_x16(s_addr + 16 * ch, pk);
+      }
       l_run = l_run * alpha + (sum0 + sum1);
-      // ---- O rescale: only after P_{j-1} V_{j-1} has retired, and only when a reference max moved
-      if (j > 0) {
-        mbar_wait(o_ready, (j - 1) & 1u);
-        if (__any_sync(0xffffffffu, alpha != 1.f)) {
-          tc_fence_after();
+      // ---- O rescale: only when a reference max moved, and only after P_{j-1} V_{j-1} has retired
+      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+        mbar_wait(o_ready((j - 1) & 1), ((j - 1) >> 1) & 1u);
+        tc_fence_after();
 #pragma unroll
-          for (int cb = 0; cb < C::DV_N; cb += 16) {
-            uint32_t r[16];
-            tmem_ld_32x32b_x16(tmem_o + lane_field + cb, r);
-            tmem_ld_wait();
+        for (int cb = 0; cb < C::DV_N; cb += 16) {
+          uint32_t ro[16];
+          tmem_ld_32x32b_x16(tmem_o + lane_field + cb, ro);
+          tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-            tmem_st_32x32b_x16(tmem_o + lane_field + cb, r);
-          }
+          for (int i = 0; i < 16; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
+          tmem_st_32x32b_x16(tmem_o + lane_field + cb, ro);
         }
       }
       tmem_st_wait();
@@ -275,7 +282,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
       if (lane == 0) mbar_arrive(p_full(j & 1));
     }
     // ---- epilogue: O / l -> fp16 -> o[b, row, h*d : h*d + d]
-    mbar_wait(o_ready, (nkv - 1) & 1u);
+    mbar_wait(o_ready((nkv - 1) & 1), ((nkv - 1) >> 1) & 1u);
     tc_fence_after();
     const float inv = 1.f / l_run;
     __half* orow = p.o + (static_cast<size_t>(b) * p.L + row) * p.C + h * p.d;

@@ -152,6 +152,11 @@ normalize_split_kernel(const __half* __restrict__ x, long long x_bs, const int* 
     }
     ss = group_sum<G>(ss);
     const float nrm = __half2float(__float2half_rn(sqrtf(ss)));
+    // x / nrm, correctly rounded, with ONE IEEE division per row: r = RN(1/nrm), q0 = RN(x r),
+    // rem = x - q0 nrm (exact, FMA), q = RN(q0 + rem r) is RN(x / nrm) (Markstein) — checked exhaustively over
+    // all fp16 numerators x 3000 fp16 norms in tests/test_host_cpu.py.  Sub-normal norms take the plain division.
+    const bool fast = nrm >= 6.103515625e-05f;
+    const float rinv = 1.0f / nrm;
 #pragma unroll
     for (int i = 0; i < P; ++i) {
       if (live && sub + G * i < vecs) {
@@ -159,7 +164,16 @@ normalize_split_kernel(const __half* __restrict__ x, long long x_bs, const int* 
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float2 f = __half22float2(h[e]);
-          h[e] = __halves2half2(__float2half_rn(f.x / nrm), __float2half_rn(f.y / nrm));
+          float qx, qy;
+          if (fast) {
+            const float q0x = __fmul_rn(f.x, rinv), q0y = __fmul_rn(f.y, rinv);
+            qx = __fmaf_rn(__fmaf_rn(-q0x, nrm, f.x), rinv, q0x);
+            qy = __fmaf_rn(__fmaf_rn(-q0y, nrm, f.y), rinv, q0y);
+          } else {
+            qx = f.x / nrm;
+            qy = f.y / nrm;
+          }
+          h[e] = __halves2half2(__float2half_rn(qx), __float2half_rn(qy));
         }
         st_16(dst + (sub + G * i) * 8, v[i]);
       }
