@@ -6,9 +6,8 @@
 //
 // Flash-attention kernel, one CTA per (128-row query tile, head, sample), 192 threads, two CTAs per SM
 // (256 TMEM columns, <= 97 KB of shared memory each):
-//   warp 0      TMA producer: Q tile once, then K/V tiles of BKV keys through a ring.  Q, K and V are read straight
-//               out of the [B*L, 3C] projection output through rank-4 tensor maps (head_dim, token, head, sample);
-//               columns beyond head_dim are zero-filled by TMA.
+//   warp 0      TMA producer: Q tile once, then K/V tiles of BKV keys through a ring, from the head-major padded
+//               q/k/v buffers written by the projection epilogue (a tile = one contiguous run of cache lines).
 //   warp 1      MMA issuer: S_j = Q K_j^T (A, B from shared memory, K-major; only ceil(d/16) K steps) into one of
 //               TWO score buffers, and O += P_j V_j with A = P_j read from TENSOR MEMORY and B = V_j read MN-major
 //               from shared memory (no transposed copy of V).  S_{j+1} is issued before P_j is awaited, so the
@@ -22,14 +21,78 @@
 // For head_dim 40 the kernel is bound by the exponential (MUFU.EX2, 16/clk/SM), not by the tensor pipe.
 // TMEM (256 columns): S0/P0 [0,BKV) | S1/P1 [BKV,2 BKV) | O [2 BKV, 2 BKV + 16*KSTEPS); BKV = 96 keys per tile when
 // that fits (head_dim <= 64), else 64.
-#include "common.cuh"
-#include "ptx.cuh"
+#include "gemm_sm100.cuh"
 
 extern "C" int vtm_linear_f16(const void*, const void*, const void*, int32_t, int32_t, int32_t, void*, int64_t,
                               void*);
 
 namespace vtm {
 namespace {
+
+// ---------------------------------------------------------------------------------------------------------
+// QKV projection epilogue: writes q, k, v HEAD-MAJOR with rows padded to DP = 64 or 128 halfs (128 / 256 bytes):
+//   qkvh[which][b][head][l][0..DP)   (which = 0 q, 1 k, 2 v; columns >= head_dim are written as zeros)
+// so that a K or V tile of consecutive keys of one head is one contiguous run of full cache lines.  Reading
+// q/k/v in place from the [B*L, 3C] GEMM output instead makes every key row an 80-byte slice at a 1920-byte
+// pitch: ncu showed 112 M L2 requests of ~1.2 sectors each for one attention call, and the K/V feed — not the
+// softmax — bounded the kernel (profiles/r01_attention_ncu_summary.md).
+struct HeadSplitEpi {
+  __half* qkvh;
+  int M, C, H, d, L, DP;     // M = B*L rows, C = H*d
+  long long which_stride;    // B*H*L*DP
+  int row;
+
+  __device__ __forceinline__ void begin(int m_tile, int, int row_in_tile) { row = m_tile * gemm::BM + row_in_tile; }
+  __device__ __forceinline__ void tile(uint32_t taddr, int col0, int ncols) {
+    const int b = row / L, l = row - b * L;
+#pragma unroll 1
+    for (int cb = 0; cb < ncols; cb += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(taddr + cb, r);
+      tmem_ld_wait();
+      if (row < M) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {          // groups of 8 output columns never straddle a head (d % 8 == 0)
+          const int n = col0 + cb + g * 8;
+          if (n < 3 * C) {
+            const int which = n / C, c = n - which * C;
+            const int head = c / d, e = c - head * d;
+            __half* dst = qkvh + which * which_stride + ((static_cast<long long>(b) * H + head) * L + l) * DP + e;
+            uint4 v;
+            uint32_t* pv = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) pv[q] = pack_f16x2(__uint_as_float(r[g * 8 + 2 * q]), __uint_as_float(r[g * 8 + 2 * q + 1]));
+            *reinterpret_cast<uint4*>(dst) = v;
+            if (e + 8 == d) {                   // last group of this head: zero the padding columns
+              const uint4 z = make_uint4(0, 0, 0, 0);
+              for (int pe = d; pe < DP; pe += 8) *reinterpret_cast<uint4*>(dst + 8 + (pe - d)) = z;
+            }
+          }
+        }
+      }
+    }
+  }
+  __device__ __forceinline__ void end(int, int, int) {}
+};
+
+int launch_qkv_heads(const void* x, const void* w_qkv, __half* qkvh, int B, int L, int C, int H, int DP,
+                     cudaStream_t stream) {
+  int sms = 0;
+  int rc = gemm::device_sms(&sms);
+  if (rc) return rc;
+  const int M = B * L, N = 3 * C;
+  HeadSplitEpi epi;
+  epi.qkvh = qkvh; epi.M = M; epi.C = C; epi.H = H; epi.d = C / H; epi.L = L; epi.DP = DP;
+  epi.which_stride = static_cast<long long>(B) * H * L * DP; epi.row = 0;
+  CUtensorMap ta, tb;
+  rc = make_tmap_3d_f16(&ta, x, C, M, 1, C, static_cast<uint64_t>(M) * C, gemm::BK, gemm::BM);
+  if (rc) return rc;
+  rc = make_tmap_3d_f16(&tb, w_qkv, C, N, 1, C, static_cast<uint64_t>(N) * C, gemm::BK, 128);
+  if (rc) return rc;
+  gemm::Work wk;
+  wk.plan(M, N, C, 1, 128, sms, 4, 1);
+  return gemm::launch<128, HeadSplitEpi>(ta, tb, wk, epi, sms, stream);
+}
 
 constexpr int BQ = 128;    // query rows per CTA (UMMA M)
 constexpr int FA_THREADS = 192;
@@ -159,7 +222,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     // ===================== TMA producer (whole warp converged; one elected lane issues) =====================
     if (elect_one()) {
       mbar_arrive_expect_tx(q_full, C::Q_BYTES);
-      for (int a = 0; a < C::ATOMS; ++a) tma_load_4d(sQ + a * (BQ * 128), &tm_q, q_full, a * 64, q0, h, b);
+      for (int a = 0; a < C::ATOMS; ++a) tma_load_3d(sQ + a * (BQ * 128), &tm_q, q_full, a * 64, q0, b * p.H + h);
     }
     for (int j = 0; j < nkv; ++j) {
       const int s = j % STAGES;
@@ -169,9 +232,9 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
       const uint32_t sv = sk + C::TILE_BYTES;
       if (elect_one()) {
         mbar_arrive_expect_tx(k_full(s), C::TILE_BYTES);
-        for (int a = 0; a < C::ATOMS; ++a) tma_load_4d(sk + a * C::KV_ATOM, &tm_k, k_full(s), a * 64, j * BKV, h, b);
+        for (int a = 0; a < C::ATOMS; ++a) tma_load_3d(sk + a * C::KV_ATOM, &tm_k, k_full(s), a * 64, j * BKV, b * p.H + h);
         mbar_arrive_expect_tx(v_full(s), C::TILE_BYTES);
-        for (int a = 0; a < C::ATOMS; ++a) tma_load_4d(sv + a * C::KV_ATOM, &tm_v, v_full(s), a * 64, j * BKV, h, b);
+        for (int a = 0; a < C::ATOMS; ++a) tma_load_3d(sv + a * C::KV_ATOM, &tm_v, v_full(s), a * 64, j * BKV, b * p.H + h);
       }
       __syncwarp();
     }
@@ -238,28 +301,63 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
       const uint32_t s_addr = tmem_base + lane_field + (j & 1) * BKV;
       const int n_valid = p.L - j * BKV;  // keys of this tile that exist
       const bool tail = n_valid < BKV;
-      // ---- the row's scores, read from TMEM once
       constexpr int NCH = BKV / 32;
-      uint32_t r[NCH][32];
+      uint32_t r[NCH][32];   // the row's scores, read from TMEM exactly once
+      float alpha = 1.f, sum0 = 0.f, sum1 = 0.f;
+      bool redo;
+      if (j == 0 || tail) {
+        // ---- plain path (first tile: no reference yet; last tile: masked columns): max first, then exponentials
 #pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) tmem_ld_32x32b_x32(s_addr + 32 * ch, r[ch]);
-      tmem_ld_wait();
-      const float mx = tail ? fa_row_max<NCH, true>(r, n_valid) : fa_row_max<NCH, false>(r, n_valid);
-      // ---- reference max moves only when exceeded by 2^RESCALE_LOG2 (P stays <= 256, exact after the O / l rescale)
-      float alpha = 1.f;
-      if ((mx - m_ref) * c > RESCALE_LOG2) {
-        alpha = ex2_approx((m_ref - mx) * c);     // 0 on the first tile (m_ref = -inf)
-        m_ref = mx;
+        for (int ch = 0; ch < NCH; ++ch) tmem_ld_32x32b_x32(s_addr + 32 * ch, r[ch]);
+        tmem_ld_wait();
+        const float mx = tail ? fa_row_max<NCH, true>(r, n_valid) : fa_row_max<NCH, false>(r, n_valid);
+        if ((mx - m_ref) * c > RESCALE_LOG2) {
+          alpha = ex2_approx((m_ref - mx) * c);     // 0 on the first tile (m_ref = -inf)
+          m_ref = mx;
+        }
+        redo = true;                                // "redo" = compute P below with the settled reference
+      } else {
+        // ---- speculative path: the reference max moves only when exceeded by 2^RESCALE_LOG2, which is rare after
+        //      the first tiles.  So the exponentials start chunk by chunk with the CURRENT reference while the
+        //      row maximum is accumulated alongside (independent instruction streams; each TMEM load overlaps the
+        //      previous chunk's MUFU work).  P stays <= 2^8 whenever the speculation holds.
+        const float mc0 = m_ref * c;
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+        tmem_ld_32x32b_x32(s_addr, r[0]);
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          tmem_ld_wait();
+          if (ch + 1 < NCH) tmem_ld_32x32b_x32(s_addr + 32 * (ch + 1), r[ch + 1]);
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            m0 = fmaxf(m0, __uint_as_float(r[ch][i]));
+            m1 = fmaxf(m1, __uint_as_float(r[ch][i + 1]));
+            m2 = fmaxf(m2, __uint_as_float(r[ch][i + 2]));
+            m3 = fmaxf(m3, __uint_as_float(r[ch][i + 3]));
+          }
+          uint32_t pk[16];
+          fa_exp32<false>(r[ch], pk, c, mc0, 32 * ch, n_valid, sum0, sum1);
+          tmem_st_32x32b_x16(s_addr + 16 * ch, pk);
+        }
+        const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        const bool moved = (mx - m_ref) * c > RESCALE_LOG2;
+        redo = __any_sync(0xffffffffu, moved);      // warp-uniform; false in the steady state
+        if (moved) {
+          alpha = ex2_approx((m_ref - mx) * c);
+          m_ref = mx;
+        }
       }
-      const float mc = m_ref * c;
-      // ---- P over the consumed score columns
-      float sum0 = 0.f, sum1 = 0.f;
+      if (redo) {
+        const float mc = m_ref * c;
+        sum0 = 0.f;
+        sum1 = 0.f;
 #pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) {
-        uint32_t pk[16];
-        if (tail) fa_exp32<true>(r[ch], pk, c, mc, 32 * ch, n_valid, sum0, sum1);
-        else fa_exp32<false>(r[ch], pk, c, mc, 32 * ch, n_valid, sum0, sum1);
-        tmem_st_32x32b_x16(s_addr + 16 * ch, pk);
+        for (int ch = 0; ch < NCH; ++ch) {
+          uint32_t pk[16];
+          if (tail) fa_exp32<true>(r[ch], pk, c, mc, 32 * ch, n_valid, sum0, sum1);
+          else fa_exp32<false>(r[ch], pk, c, mc, 32 * ch, n_valid, sum0, sum1);
+          tmem_st_32x32b_x16(s_addr + 16 * ch, pk);
+        }
       }
       l_run = l_run * alpha + (sum0 + sum1);
       // ---- O rescale: only when a reference max moved, and only after P_{j-1} V_{j-1} has retired
@@ -319,19 +417,18 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
 }
 
 template <int KSTEPS>
-int launch_fa(const void* qkv, __half* o, int B, int L, int C, int H, int d, float scale, cudaStream_t stream) {
+int launch_fa(const void* qkvh, __half* o, int B, int L, int C, int H, int d, float scale, cudaStream_t stream) {
   using Cf = FaCfg<KSTEPS>;
   CUtensorMap tq, tk, tv;
-  const uint64_t dims[4] = {static_cast<uint64_t>(d), static_cast<uint64_t>(L), static_cast<uint64_t>(H),
-                            static_cast<uint64_t>(B)};
-  const uint64_t strides[3] = {static_cast<uint64_t>(3) * C, static_cast<uint64_t>(d),
-                               static_cast<uint64_t>(L) * 3 * C};
-  const __half* base = static_cast<const __half*>(qkv);
-  int rc = make_tmap_4d_f16(&tq, base, dims, strides, 64, BQ);
+  const int DP = Cf::ATOMS * 64;                       // padded head_dim of the head-major q/k/v buffers
+  const uint64_t BH = static_cast<uint64_t>(B) * H;
+  const __half* base = static_cast<const __half*>(qkvh);
+  const uint64_t which_stride = BH * L * DP;
+  int rc = make_tmap_3d_f16(&tq, base, DP, L, BH, DP, static_cast<uint64_t>(L) * DP, 64, BQ);
   if (rc) return rc;
-  rc = make_tmap_4d_f16(&tk, base + C, dims, strides, 64, Cf::BKV);
+  rc = make_tmap_3d_f16(&tk, base + which_stride, DP, L, BH, DP, static_cast<uint64_t>(L) * DP, 64, Cf::BKV);
   if (rc) return rc;
-  rc = make_tmap_4d_f16(&tv, base + 2 * C, dims, strides, 64, Cf::BKV);
+  rc = make_tmap_3d_f16(&tv, base + 2 * which_stride, DP, L, BH, DP, static_cast<uint64_t>(L) * DP, 64, Cf::BKV);
   if (rc) return rc;
   rc = cuda_rc(cudaFuncSetAttribute(flash_attn_kernel<KSTEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(Cf::SMEM_BYTES)));
@@ -351,7 +448,11 @@ int launch_fa(const void* qkv, __half* o, int B, int L, int C, int H, int d, flo
 extern "C" size_t vtm_attention_workspace_bytes(int32_t B, int32_t L, int32_t C, int32_t heads) {
   (void)heads;
   if (B <= 0 || L <= 0 || C <= 0) return 0;
-  return static_cast<size_t>(B) * L * C * 2 * 4;  // qkv [B*L, 3C] + o [B*L, C], fp16
+  if (heads <= 0 || C % heads != 0) return 0;
+  const int d = C / heads;
+  const size_t DP = d <= 64 ? 64 : 128;
+  // q/k/v head-major [3][B][H][L][DP] + o [B*L, C], fp16
+  return (static_cast<size_t>(3) * B * heads * L * DP + static_cast<size_t>(B) * L * C) * 2;
 }
 
 extern "C" int vtm_attention(const void* x_dev, const void* w_qkv_dev, const void* w_o_dev, const void* b_o_dev,
@@ -365,10 +466,11 @@ extern "C" int vtm_attention(const void* x_dev, const void* w_qkv_dev, const voi
   if (d > 128) return VTM_E_UNSUPPORTED;
   if (ws_bytes < vtm_attention_workspace_bytes(B, L, C, heads)) return VTM_E_WS;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int DP = d <= 64 ? 64 : 128;
   __half* qkv = static_cast<__half*>(ws_dev);
-  __half* o = qkv + static_cast<size_t>(B) * L * 3 * C;
+  __half* o = qkv + static_cast<size_t>(3) * B * heads * L * DP;
   const int M = B * L;
-  int rc = vtm_linear_f16(x_dev, w_qkv_dev, nullptr, M, 3 * C, C, qkv, 3 * C, stream_);
+  int rc = launch_qkv_heads(x_dev, w_qkv_dev, qkv, B, L, C, heads, DP, stream);
   if (rc) return rc;
   const int ksteps = (d + 15) / 16;
   switch (ksteps) {
