@@ -139,14 +139,27 @@ __device__ __forceinline__ float fa_row_max(const uint32_t (&r)[NCH][32], int n_
   }
   return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 }
-// P = exp2(s*c - mc) for 32 scores -> 16 packed fp16 pairs; accumulates the fp32 row sum.
+// P = exp2(s*c - mc) for 32 scores -> 16 packed fp16 pairs; accumulates the fp32 row sum.  The kernel is bound by
+// MUFU.EX2 (16/clk/SM) for small head_dim, so every POLY_EVERY-th pair is evaluated on the FMA pipe instead
+// (ex2_poly3): the two pipes run side by side.
+#ifndef VTM_FA_POLY_EVERY
+#define VTM_FA_POLY_EVERY 4
+#endif
 template <bool TAIL>
 __device__ __forceinline__ void fa_exp32(const uint32_t (&r)[32], uint32_t (&pk)[16], float c, float mc, int col0,
                                          int n_valid, float& sum0, float& sum1) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * i]), c, -mc));
-    float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), c, -mc));
+    const float x0 = fmaf(__uint_as_float(r[2 * i]), c, -mc);
+    const float x1 = fmaf(__uint_as_float(r[2 * i + 1]), c, -mc);
+    float p0, p1;
+    if (VTM_FA_POLY_EVERY > 0 && (i % VTM_FA_POLY_EVERY) == VTM_FA_POLY_EVERY - 1) {
+      p0 = ex2_poly3(x0);
+      p1 = ex2_poly3(x1);
+    } else {
+      p0 = ex2_approx(x0);
+      p1 = ex2_approx(x1);
+    }
     if (TAIL) {
       if (col0 + 2 * i >= n_valid) p0 = 0.f;
       if (col0 + 2 * i + 1 >= n_valid) p1 = 0.f;
