@@ -124,10 +124,11 @@ extern "C" int vtm_sim_argmax(const void* a_dev, const void* b_dev, int32_t B, i
   if (rc) return rc;
 
   // Split the dst sweep so that the persistent grid is balanced (>= 16 work items per SM when the
-  // problem allows), each item still >= 4 dst tiles long.  The TMA/MMA pipeline runs straight across
-  // work-item boundaries, so finer items cost only one 8-byte atomic per src row.
+  // problem allows).  The TMA/MMA pipeline runs straight across work-item boundaries, so finer items cost
+  // only one 8-byte atomic per src row per item — even single-tile items pay off on the small levels
+  // (ds2 level 2: 48 (block, sample) pairs for 148 SMs).
   gemm::Work wk;
-  wk.plan(Ns, Nd, C, B, BN, sms, 16, 4);
+  wk.plan(Ns, Nd, C, B, BN, sms, 16, 1);
   ArgmaxEpi epi;
   epi.keys = reinterpret_cast<unsigned long long*>(keys_out_dev);
   epi.Ns = Ns; epi.Nd = Nd; epi.align_batch = align_batch ? 1 : 0;

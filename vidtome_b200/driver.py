@@ -102,8 +102,10 @@ class ChunkedDenoiser:
     def step(self, x: torch.Tensor, i: int) -> torch.Tensor:
         noises = torch.zeros_like(x)
         for chunk in self.get_chunks(len(x)):
-            idx = chunk.to(x.device)
-            noises[idx] = self.pred_noise(x[idx], self.timesteps[i])
+            # chunks are contiguous frame ranges (possibly visited in another order): slice instead of indexing with
+            # a host tensor, which would cost a synchronous host->device copy per chunk per step
+            lo, hi = int(chunk[0]), int(chunk[-1]) + 1
+            noises[lo:hi] = self.pred_noise(x[lo:hi], self.timesteps[i])
         x = self.pred_next_x(x, noises, i)
         if self.merge_global:
             patch.update_patch(self.unet, global_tokens=None)                # generate.py:233-236
