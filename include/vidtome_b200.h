@@ -191,7 +191,8 @@ int vtm_unmerge_add(const void* y_dev, int64_t y_batch_stride, const int32_t* ma
  * per-head softmax(q k^T * scale) v, heads re-joined, y = o Wo^T + bo.
  *   x_dev [B, L, C] fp16; w_qkv_dev [3C, C] fp16 (rows: Wq | Wk | Wv, torch Linear layout);
  *   w_o_dev [C, C] fp16; b_o_dev [C] fp16 (may be NULL); heads * head_dim == C; head_dim <= 160
- *   y_dev [B, L, C] fp16; ws_dev workspace of vtm_attention_workspace_bytes(B, L, C, heads) bytes.
+ *   y_dev [B, L, C] fp16; ws_dev workspace of vtm_attention_workspace_bytes(B, L, C, heads) bytes (q/k/v head-major
+ *   with rows padded to 64 or 128 halfs, plus the attention output before the out projection).
  */
 size_t vtm_attention_workspace_bytes(int32_t B, int32_t L, int32_t C, int32_t heads);
 int vtm_attention(const void* x_dev, const void* w_qkv_dev, const void* w_o_dev, const void* b_o_dev,
