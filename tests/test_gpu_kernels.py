@@ -96,7 +96,7 @@ def test_normalize_split_rowmap():
     (2, 515, 5000, 320, False),    # many dst tiles -> split dst sweeps + atomic combine
     (1, 130, 257, 72, False),      # K tail (72 = 64 + 8), 1-row / 1-column tails
 ])
-def test_sim_argmax_bit_exact_on_exact_inputs(B, Ns, Nd, C, align):
+def test_sim_argmax_bit_exact_on_exact_inputs(B, Ns, Nd, C, align, ka_variant):
     ops = _ops()
     rng = np.random.default_rng(B * 1000 + Ns)
     nnz = min(64, C // 2)
@@ -107,6 +107,71 @@ def test_sim_argmax_bit_exact_on_exact_inputs(B, Ns, Nd, C, align):
     score, arg = ops.keys_to_score_arg(keys)
     np.testing.assert_array_equal(score.cpu().numpy().view(np.uint16), mx.view(np.uint16))
     np.testing.assert_array_equal(arg.cpu().numpy(), idx)
+
+
+@pytest.fixture(params=["cta", "cta_pair"])
+def ka_variant(request, monkeypatch):
+    """KA's default kernel and its CTA-pair (cta_group::2) build, selected per call by VTM_KA_2CTA."""
+    if request.param == "cta_pair":
+        monkeypatch.setenv("VTM_KA_2CTA", "1")
+    else:
+        monkeypatch.delenv("VTM_KA_2CTA", raising=False)
+    return request.param
+
+
+@pytest.mark.parametrize("align", [False, True])
+def test_sim_argmax_equal_maxima_across_dst_ranges(align, ka_variant):
+    """The epilogue filters on the maximum other dst ranges have already published.  Every dst row here occurs
+    many times across the whole sweep (and in both samples), so the winning score is tied across work items that
+    run in arbitrary order: the smallest dst index must still win, bit for bit."""
+    ops = _ops()
+    rng = np.random.default_rng(11)
+    B, Ns, Nd, C = 2, 700, 6144, 320
+    a = _exact_tokens(rng, (B, Ns, C))
+    pool = _exact_tokens(rng, (1, 96, C))[0]
+    pick = rng.integers(0, 96, size=(B, Nd))
+    b = pool[pick]
+    if align:
+        b[1] = b[0][::-1]                      # the same rows again in the second sample, other order
+    _, mx, idx = _oracle_node(a, b, align)
+    keys = ops.sim_argmax(torch.from_numpy(a).cuda(), torch.from_numpy(np.ascontiguousarray(b)).cuda(), align)
+    score, arg = ops.keys_to_score_arg(keys)
+    np.testing.assert_array_equal(score.cpu().numpy().view(np.uint16), mx.view(np.uint16))
+    np.testing.assert_array_equal(arg.cpu().numpy(), idx)
+
+
+def test_sim_argmax_nonpositive_and_zero_scores(ka_variant):
+    """Rows whose best score is negative, +0 or -0 (threshold stepping around zero, merge.py:112 semantics)."""
+    ops = _ops()
+    rng = np.random.default_rng(12)
+    B, Ns, Nd, C = 1, 260, 2304, 128
+    b = np.abs(_exact_tokens(rng, (B, Nd, C, ), nnz=48))
+    a = -np.abs(_exact_tokens(rng, (B, Ns, C), nnz=48))   # every score <= 0; supports overlap, so most are < 0
+    a[0, :40] = 0                                         # all scores +0 for these src rows
+    for zero_rows in (False, True):
+        if zero_rows:
+            b[0, 1500::211] = 0                           # late zero dst rows: -0 beats the negative scores so far
+        a16, b16 = a.astype(np.float16), b.astype(np.float16)
+        s, mx, idx = _oracle_node(a16, b16, False)
+        assert zero_rows or (mx[0, 40:] < 0).all()
+        keys = ops.sim_argmax(torch.from_numpy(a16).cuda(), torch.from_numpy(b16).cuda(), False)
+        score, arg = ops.keys_to_score_arg(keys)
+        assert np.array_equal(score.cpu().numpy().astype(np.float32), mx.astype(np.float32))     # -0 == +0
+        np.testing.assert_array_equal(arg.cpu().numpy(), idx)
+
+
+def test_sim_argmax_cta_pair_equals_default(monkeypatch):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for (B, Ns, Nd, C, align) in [(2, 3072, 1024, 320, False), (2, 1000, 5000, 640, True), (3, 129, 257, 1280, False),
+                                  (1, 77, 33, 64, False)]:
+        a = torch.randn((B, Ns, C), generator=g, device="cuda").half()
+        b = torch.randn((B, Nd, C), generator=g, device="cuda").half()
+        monkeypatch.delenv("VTM_KA_2CTA", raising=False)
+        k1 = ops.sim_argmax(a, b, align)
+        monkeypatch.setenv("VTM_KA_2CTA", "1")
+        k2 = ops.sim_argmax(a, b, align)
+        assert torch.equal(k1, k2)
 
 
 @pytest.mark.parametrize("align", [False, True])

@@ -121,6 +121,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+#if defined(VTM_EXP_NO_TMA)
+      int exp_chunks = 0;
+#endif
       for (int w = blockIdx.x; w < wk.total; w += gridDim.x) {
         int m_tile, b, nt0, nt1;
         wk.decode(w, &m_tile, &b, &nt0, &nt1);
@@ -128,9 +131,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           for (int kc = 0; kc < wk.k_chunks; ++kc) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+#if defined(VTM_EXP_NO_TMA)   // timing experiment (tools/ubench/ka_bubbles.cu): only the first ring fill is loaded
+            if (exp_chunks++ >= STAGES) { mbar_arrive(full_bar(stage)); } else
+#endif
+            {
             mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
             tma_load_3d(sa, &tmap_a, full_bar(stage), kc * BK, m_tile * BM, b);
             tma_load_3d(sa + A_BYTES, &tmap_b, full_bar(stage), kc * BK, nt * BN, b);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
@@ -153,7 +161,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + as * BN;
           for (int kc = 0; kc < wk.k_chunks; ++kc) {
+#if !defined(VTM_EXP_NO_FULL_WAIT)   // timing experiment: MMA does not wait for the loads
             mbar_wait(full_bar(stage), phase);
+#endif
             tc_fence_after();
             const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
             const uint64_t adesc = umma_desc_sw128_kmajor(sa);
@@ -188,7 +198,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         tc_fence_after();
         const uint32_t taddr =
             tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + half * (BN / 2);
+#if !defined(VTM_EXP_NO_EPI)   // timing experiment: accumulators are not read
         e.tile(taddr, nt * BN + half * (BN / 2), BN / 2);
+#endif
         // every tcgen05.ld issued by tile() has been waited on (tcgen05.wait::ld) before it returns
         tc_fence_before();
         __syncwarp();

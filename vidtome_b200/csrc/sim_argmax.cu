@@ -8,7 +8,9 @@
 // accumulators from TMEM (one src row per thread), rounds to fp16 and keeps a running (max, first
 // arg).  Partial results are merged across dst ranges / samples with a 64-bit atomicMax on a packed
 // (ordered score, ~arg) key, which realises exactly "largest score, then smallest index".
-#include "gemm_sm100.cuh"
+#include <stdlib.h>
+
+#include "gemm_sm100_2cta.cuh"
 
 namespace vtm {
 namespace {
@@ -18,32 +20,72 @@ constexpr int BN = 256;
 struct ArgmaxEpi {
   unsigned long long* keys;  // [B', Ns]
   int Ns, Nd, align_batch;
-  float best;
+  float best;          // running maximum of this work item, or the entry threshold while best_idx is "none"
   uint32_t best_idx;
 
-  __device__ __forceinline__ void begin(int, int, int) {
+  // A work item starts from what other items (other dst ranges / samples of the same src rows) have already
+  // published: scores below the published maximum cannot win, so they are filtered with one FMNMX3 per two
+  // accumulators and the per-element scan below runs only for the rare 64-column group that holds a candidate.
+  // The threshold is the fp16 value just BELOW the published maximum, so an equal score still becomes a candidate
+  // and the packed-key atomicMax resolves the tie towards the smaller dst index exactly as before.  Any stale
+  // value read here is a valid (lower) threshold: published keys only grow.
+  __device__ __forceinline__ void begin(int m_tile, int b, int row_in_tile) {
     best = -INFINITY;
     best_idx = 0xFFFFFFFFu;
+    const int row = m_tile * gemm::BM + row_in_tile;
+    if (row < Ns) {
+      const size_t o = (align_batch ? 0 : static_cast<size_t>(b) * Ns) + row;
+      const unsigned long long k = *reinterpret_cast<const volatile unsigned long long*>(keys + o);
+      uint32_t ord = static_cast<uint32_t>(k >> 32);
+      if (k != 0ull && ord > 0x0400u) {          // published and above -inf
+        ord -= 1u;
+        if (ord == 0x7FFFu) ord = 0x7FFEu;       // below +0 comes -0, which compares equal: step once more
+        best = __half2float(__ushort_as_half(static_cast<unsigned short>(ordered_to_half_bits(ord))));
+      }
+    }
+  }
+  static __device__ __forceinline__ float round_f16(float x) { return __half2float(__float2half_rn(x)); }
+  __device__ __forceinline__ void scan(const uint32_t (&r)[64], int base, int n_valid) {
+#pragma unroll
+    for (int c = 0; c < 64; ++c) {
+      const float hv = round_f16(__uint_as_float(r[c]));
+      if (c < n_valid && hv > best) { best = hv; best_idx = static_cast<uint32_t>(base + c); }
+    }
   }
   __device__ __forceinline__ void tile(uint32_t taddr, int col0, int ncols) {
     const int n_valid = Nd - col0;  // columns of this slice that are real dst tokens
 #pragma unroll 1
-    for (int cb = 0; cb < ncols; cb += 32) {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(taddr + cb, r);
+    for (int cb = 0; cb < ncols; cb += 64) {
+      uint32_t r[64];
+      tmem_ld_32x32b_x64(taddr + cb, r);
       tmem_ld_wait();
-      if (cb + 32 <= n_valid) {
+      if (cb + 64 <= n_valid) {
+        // Rounding to fp16 is monotonic, so max(round(x_i)) == round(max(x_i)): filter on the fp32 maxima of four
+        // 16-column groups (8 FMNMX3 each).  The branch is warp-wide, hence the fine groups: a candidate in one
+        // lane costs the warp a 16-element scan, not a 64-element one.
+        float g[4];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const float hv = __half2float(__float2half_rn(__uint_as_float(r[c])));
-          if (hv > best) { best = hv; best_idx = static_cast<uint32_t>(col0 + cb + c); }
-        }
-      } else {
+        for (int q = 0; q < 4; ++q) {
+          float m = fmax3(__uint_as_float(r[16 * q]), __uint_as_float(r[16 * q + 1]), __uint_as_float(r[16 * q + 2]));
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const float hv = __half2float(__float2half_rn(__uint_as_float(r[c])));
-          if (cb + c < n_valid && hv > best) { best = hv; best_idx = static_cast<uint32_t>(col0 + cb + c); }
+          for (int c = 3; c + 1 < 16; c += 2)
+            m = fmax3(m, __uint_as_float(r[16 * q + c]), __uint_as_float(r[16 * q + c + 1]));
+          g[q] = fmaxf(m, __uint_as_float(r[16 * q + 15]));
         }
+        if (round_f16(fmax3(fmaxf(g[0], g[1]), g[2], g[3])) > best) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (round_f16(g[q]) > best) {      // ascending groups and strict '>' keep the first index among equals
+#pragma unroll
+              for (int c = 0; c < 16; ++c) {
+                const float hv = round_f16(__uint_as_float(r[16 * q + c]));
+                if (hv > best) { best = hv; best_idx = static_cast<uint32_t>(col0 + cb + 16 * q + c); }
+              }
+            }
+          }
+        }
+      } else if (cb < n_valid) {
+        scan(r, col0 + cb, n_valid - cb);
       }
     }
   }
@@ -133,6 +175,24 @@ extern "C" int vtm_sim_argmax(const void* a_dev, const void* b_dev, int32_t B, i
   epi.keys = reinterpret_cast<unsigned long long*>(keys_out_dev);
   epi.Ns = Ns; epi.Nd = Nd; epi.align_batch = align_batch ? 1 : 0;
   epi.best = 0.f; epi.best_idx = 0;
+  if (getenv("VTM_KA_2CTA") != nullptr) {
+    // CTA-pair variant: 256-row src blocks per pair, B tensor map with 128-row boxes (each CTA loads half a tile)
+    CUtensorMap tb2;
+    rc = make_tmap_3d_f16(&tb2, b_dev, C, Nd, B, C, static_cast<uint64_t>(Nd) * C, gemm::BK, 128);
+    if (rc) return rc;
+    gemm::Work wk2;
+    wk2.plan(Ns, Nd, C, B, BN, sms / 2, 16, 1);
+    wk2.m_tiles = (Ns + 255) / 256;
+    {  // re-plan the dst split for pair blocks
+      const long long base = static_cast<long long>(wk2.m_tiles) * B;
+      int sp = 1;
+      while (base * sp < 16ll * (sms / 2) && sp * 2 <= wk2.n_tiles) sp *= 2;
+      wk2.tiles_per_split = (wk2.n_tiles + sp - 1) / sp;
+      wk2.n_splits = (wk2.n_tiles + wk2.tiles_per_split - 1) / wk2.tiles_per_split;
+      wk2.total = static_cast<int>(base * wk2.n_splits);
+    }
+    return gemm::launch_2cta<ArgmaxEpi>(ta, tb2, wk2, epi, sms, stream);
+  }
   return gemm::launch<BN, ArgmaxEpi>(ta, tb, wk, epi, sms, stream);
 }
 
