@@ -43,7 +43,10 @@ extern "C" {
  *     sequence = [unm_pre carried tokens | F frames of tnum tokens]; a frame f is dst iff
  *     f % stride == randf; dst = those frames (ascending) followed by the unm_pre carried tokens;
  *     src = the remaining frames (ascending).  stride = min(target_stride, F) (merge.py:55),
- *     randf is the host-drawn torch.randint value (merge.py:56-57).
+ *     randf is the torch.randint value (merge.py:56-57): either drawn to the host (`randf`) or left on the
+ *     device (`randf_dev` != NULL: the kernels read *randf_dev, and `randf` is ignored).  The device form lets
+ *     a whole denoising step be captured in a CUDA graph whose replays draw fresh values; it requires
+ *     F % stride == 0, so that the src / dst counts do not depend on the draw (else VTM_E_SPLIT).
  *   mode 1 (global, prefix/suffix) — bipartite_soft_matching_2s, vidtome/merge.py:371-379:
  *     src = positions [0, src_len), dst = positions [src_len, N).
  */
@@ -56,6 +59,7 @@ typedef struct vtm_split {
   int32_t stride;
   int32_t randf;
   int32_t src_len;
+  const int32_t* randf_dev; /* optional device-resident randf (mode 0), NULL = use `randf` */
 } vtm_split_t;
 
 /* Library version (VTM_VERSION).  Pure host. */

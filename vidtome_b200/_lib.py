@@ -17,17 +17,26 @@ LIB_PATH = os.path.join(_HERE, "libvidtome_b200.so")
 class VtmSplit(C.Structure):
     """struct vtm_split (include/vidtome_b200.h)."""
     _fields_ = [(n, C.c_int32) for n in
-                ("mode", "N", "unm_pre", "F", "tnum", "stride", "randf", "src_len")]
+                ("mode", "N", "unm_pre", "F", "tnum", "stride", "randf", "src_len")] + [("randf_dev", C.c_void_p)]
 
     @classmethod
-    def local(cls, N: int, unm_pre: int, F: int, target_stride: int, randf: int) -> "VtmSplit":
+    def local(cls, N: int, unm_pre: int, F: int, target_stride: int, randf) -> "VtmSplit":
+        """`randf`: the drawn int, or a 1-element int32 CUDA tensor holding it (kept alive on the descriptor) when
+        the draw stays on the device (CUDA-graph capture; needs F % stride == 0)."""
         tnum = (N - unm_pre) // F                      # merge.py:43
         stride = min(target_stride, F)                 # merge.py:55
-        return cls(0, N, unm_pre, F, tnum, stride, randf, 0)
+        if isinstance(randf, int):
+            return cls(0, N, unm_pre, F, tnum, stride, randf, 0, None)
+        import torch
+        if not (isinstance(randf, torch.Tensor) and randf.is_cuda and randf.dtype == torch.int32 and randf.numel() == 1):
+            raise RuntimeError("VtmSplit.local: randf must be an int or a 1-element int32 CUDA tensor")
+        sp = cls(0, N, unm_pre, F, tnum, stride, 0, 0, randf.data_ptr())
+        sp._keepalive = randf
+        return sp
 
     @classmethod
     def prefix(cls, N: int, src_len: int) -> "VtmSplit":
-        return cls(1, N, 0, 0, 0, 0, 0, src_len)
+        return cls(1, N, 0, 0, 0, 0, 0, src_len, None)
 
 
 _vp, _i32, _i64, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t

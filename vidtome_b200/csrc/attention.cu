@@ -21,6 +21,8 @@
 // For head_dim 40 the kernel is bound by the exponential (MUFU.EX2, 16/clk/SM), not by the tensor pipe.
 // TMEM (256 columns): S0/P0 [0,BKV) | S1/P1 [BKV,2 BKV) | O [2 BKV, 2 BKV + 16*KSTEPS); BKV = 96 keys per tile when
 // that fits (head_dim <= 64), else 64.
+#include <stdlib.h>
+
 #include "gemm_sm100.cuh"
 
 extern "C" int vtm_linear_f16(const void*, const void*, const void*, int32_t, int32_t, int32_t, void*, int64_t,
@@ -37,39 +39,57 @@ namespace {
 // pitch: ncu showed 112 M L2 requests of ~1.2 sectors each for one attention call, and the K/V feed — not the
 // softmax — bounded the kernel (profiles/r01_attention_ncu_summary.md).
 struct HeadSplitEpi {
+  static constexpr uint32_t SCRATCH_PER_WARP = gemm::STAGE_STORE_BYTES;
   __half* qkvh;
-  int M, C, H, d, L, DP;     // M = B*L rows, C = H*d
+  int M, C, H, d, L, DP, nb; // M = nb*L rows, C = H*d
   long long which_stride;    // B*H*L*DP
-  int row;
+  int row0;                  // first of the warp's 32 rows
+  uint32_t scratch;
 
-  __device__ __forceinline__ void begin(int m_tile, int, int row_in_tile) { row = m_tile * gemm::BM + row_in_tile; }
+  __device__ __forceinline__ void set_scratch(uint32_t a) { scratch = a; }
+  // Integer divisions are ~40 dependent instructions each and this epilogue has only two warps per scheduler to
+  // hide them (they dominated the first version of this kernel): (sample, position) of a row is divided once per
+  // work item and stepped from there, (q/k/v, head, column) once per 64-column chunk.
+  int b0, l0;                // (sample, position) of row row0 + lane / 8, this lane's first row in the store phase
+  __device__ __forceinline__ void begin(int m_tile, int, int row_in_tile) {
+    row0 = m_tile * gemm::BM + (row_in_tile & ~31);
+    const int r = row0 + ((row_in_tile & 31) >> 3);
+    b0 = r / L;
+    l0 = r - b0 * L;
+  }
   __device__ __forceinline__ void tile(uint32_t taddr, int col0, int ncols) {
-    const int b = row / L, l = row - b * L;
 #pragma unroll 1
-    for (int cb = 0; cb < ncols; cb += 32) {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(taddr + cb, r);
+    for (int cb = 0; cb < ncols; cb += 64) {
+      uint32_t r[64];
+      tmem_ld_32x32b_x64(taddr + cb, r);
       tmem_ld_wait();
-      if (row < M) {
+      uint32_t pk[32];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {          // groups of 8 output columns never straddle a head (d % 8 == 0)
-          const int n = col0 + cb + g * 8;
-          if (n < 3 * C) {
-            const int which = n / C, c = n - which * C;
-            const int head = c / d, e = c - head * d;
-            __half* dst = qkvh + which * which_stride + ((static_cast<long long>(b) * H + head) * L + l) * DP + e;
-            uint4 v;
-            uint32_t* pv = reinterpret_cast<uint32_t*>(&v);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) pv[q] = pack_f16x2(__uint_as_float(r[g * 8 + 2 * q]), __uint_as_float(r[g * 8 + 2 * q + 1]));
-            *reinterpret_cast<uint4*>(dst) = v;
-            if (e + 8 == d) {                   // last group of this head: zero the padding columns
-              const uint4 z = make_uint4(0, 0, 0, 0);
-              for (int pe = d; pe < DP; pe += 8) *reinterpret_cast<uint4*>(dst + 8 + (pe - d)) = z;
-            }
+      for (int e = 0; e < 32; ++e) pk[e] = pack_f16x2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
+      // this lane's 8 columns in the store phase: the same for all of its rows
+      const int n = col0 + cb + (threadIdx.x & 7) * 8;       // groups of 8 columns never straddle a head (d % 8 == 0)
+      const bool n_ok = n < 3 * C;
+      const int which = n / C, c = n - which * C;
+      const int head = c / d, e0 = c - head * d;
+      const bool last_group = e0 + 8 == d;                   // then this lane also zeroes the head's padding columns
+      // dst(b, l) = base + (b H L + l) DP: stepped by 4 rows per store (plus (H - 1) L DP when crossing a sample)
+      __half* dst = qkvh + which * which_stride + static_cast<long long>(head) * L * DP + e0 +
+                    (static_cast<long long>(b0) * H * L + l0) * DP;
+      const long long row_step = 4ll * DP, sample_step = static_cast<long long>(H - 1) * L * DP;
+      int bb = b0, ll = l0;
+      // staged through shared memory (gemm::warp_store_rows64): eight lanes write 64 consecutive columns of one row
+      gemm::warp_store_rows64(scratch, pk, [&](int, int, const uint4& v) {
+        if (bb < nb && n_ok) {
+          *reinterpret_cast<uint4*>(dst) = v;
+          if (last_group) {
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            for (int pe = d; pe < DP; pe += 8) *reinterpret_cast<uint4*>(dst + 8 + (pe - d)) = z;
           }
         }
-      }
+        ll += 4;                                              // next row of this lane: 4 further down
+        dst += row_step;
+        while (ll >= L) { ll -= L; ++bb; dst += sample_step; }
+      });
     }
   }
   __device__ __forceinline__ void end(int, int, int) {}
@@ -83,14 +103,14 @@ int launch_qkv_heads(const void* x, const void* w_qkv, __half* qkvh, int B, int 
   const int M = B * L, N = 3 * C;
   HeadSplitEpi epi;
   epi.qkvh = qkvh; epi.M = M; epi.C = C; epi.H = H; epi.d = C / H; epi.L = L; epi.DP = DP;
-  epi.which_stride = static_cast<long long>(B) * H * L * DP; epi.row = 0;
+  epi.which_stride = static_cast<long long>(B) * H * L * DP; epi.row0 = 0; epi.scratch = 0; epi.b0 = 0; epi.l0 = 0; epi.nb = B;
   CUtensorMap ta, tb;
   rc = make_tmap_3d_f16(&ta, x, C, M, 1, C, static_cast<uint64_t>(M) * C, gemm::BK, gemm::BM);
   if (rc) return rc;
   rc = make_tmap_3d_f16(&tb, w_qkv, C, N, 1, C, static_cast<uint64_t>(N) * C, gemm::BK, 128);
   if (rc) return rc;
   gemm::Work wk;
-  wk.plan(M, N, C, 1, 128, sms, 4, 1);
+  wk.plan(M, N, C, 1, 128, sms, 16, 1);
   return gemm::launch<128, HeadSplitEpi>(ta, tb, wk, epi, sms, stream);
 }
 
@@ -102,6 +122,12 @@ struct FaParams {
   int L, H, d, C;
   float scale_log2;   // softmax scale * log2(e)
   __half* o;          // [B*L, C]
+  // Work decomposition (see launch_fa): units [0, n_full) are whole (query tile, head, sample) problems; each of
+  // the remaining tiles is cut into `splits` key ranges whose un-normalised results go to part_o / part_ml and
+  // are merged by fa_combine_kernel.
+  int n_qtiles, n_full, splits;
+  float* part_o;      // [tile - n_full][splits][BQ][DV_N]  fp32, relative to the part's reference max
+  float2* part_ml;    // [tile - n_full][splits][BQ]        (reference max * scale_log2, denominator)
 };
 
 template <int KSTEPS>
@@ -131,10 +157,17 @@ __device__ __forceinline__ float fa_row_max(const uint32_t (&r)[NCH][32], int n_
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
       const int col = ch * 32 + i;
-      if (!TAIL || col < n_valid) m0 = fmaxf(m0, __uint_as_float(r[ch][i]));
-      if (!TAIL || col + 1 < n_valid) m1 = fmaxf(m1, __uint_as_float(r[ch][i + 1]));
-      if (!TAIL || col + 2 < n_valid) m2 = fmaxf(m2, __uint_as_float(r[ch][i + 2]));
-      if (!TAIL || col + 3 < n_valid) m3 = fmaxf(m3, __uint_as_float(r[ch][i + 3]));
+      if (!TAIL) {
+        if (i & 4) m1 = fmax3(m1, __uint_as_float(r[ch][i]), __uint_as_float(r[ch][i + 1])),
+                   m3 = fmax3(m3, __uint_as_float(r[ch][i + 2]), __uint_as_float(r[ch][i + 3]));
+        else       m0 = fmax3(m0, __uint_as_float(r[ch][i]), __uint_as_float(r[ch][i + 1])),
+                   m2 = fmax3(m2, __uint_as_float(r[ch][i + 2]), __uint_as_float(r[ch][i + 3]));
+      } else {
+        if (col < n_valid) m0 = fmaxf(m0, __uint_as_float(r[ch][i]));
+        if (col + 1 < n_valid) m1 = fmaxf(m1, __uint_as_float(r[ch][i + 1]));
+        if (col + 2 < n_valid) m2 = fmaxf(m2, __uint_as_float(r[ch][i + 2]));
+        if (col + 3 < n_valid) m3 = fmaxf(m3, __uint_as_float(r[ch][i + 3]));
+      }
     }
   }
   return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
@@ -197,10 +230,20 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * BQ;
-  const int h = blockIdx.y;
-  const int b = blockIdx.z;
-  const int nkv = (p.L + BKV - 1) / BKV;
+  // unit -> (tile, key range).  Whole tiles first, then the split ones: the split units fill the last, partial wave.
+  int tile = blockIdx.x, part = 0, nparts = 1;
+  if (tile >= p.n_full) {
+    const int v = tile - p.n_full;
+    tile = p.n_full + v / p.splits;
+    part = v % p.splits;
+    nparts = p.splits;
+  }
+  const int q0 = (tile % p.n_qtiles) * BQ;
+  const int h = (tile / p.n_qtiles) % p.H;
+  const int b = tile / (p.n_qtiles * p.H);
+  const int nkv_all = (p.L + BKV - 1) / BKV;
+  const int j_lo = static_cast<int>(static_cast<long long>(part) * nkv_all / nparts);
+  const int nkv = static_cast<int>(static_cast<long long>(part + 1) * nkv_all / nparts) - j_lo;   // >= 1
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_q);
@@ -245,9 +288,9 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
       const uint32_t sv = sk + C::TILE_BYTES;
       if (elect_one()) {
         mbar_arrive_expect_tx(k_full(s), C::TILE_BYTES);
-        for (int a = 0; a < C::ATOMS; ++a) tma_load_3d(sk + a * C::KV_ATOM, &tm_k, k_full(s), a * 64, j * BKV, b * p.H + h);
+        for (int a = 0; a < C::ATOMS; ++a) tma_load_3d(sk + a * C::KV_ATOM, &tm_k, k_full(s), a * 64, (j_lo + j) * BKV, b * p.H + h);
         mbar_arrive_expect_tx(v_full(s), C::TILE_BYTES);
-        for (int a = 0; a < C::ATOMS; ++a) tma_load_3d(sv + a * C::KV_ATOM, &tm_v, v_full(s), a * 64, j * BKV, b * p.H + h);
+        for (int a = 0; a < C::ATOMS; ++a) tma_load_3d(sv + a * C::KV_ATOM, &tm_v, v_full(s), a * 64, (j_lo + j) * BKV, b * p.H + h);
       }
       __syncwarp();
     }
@@ -312,7 +355,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
       mbar_wait(s_full(j & 1), (j >> 1) & 1u);
       tc_fence_after();
       const uint32_t s_addr = tmem_base + lane_field + (j & 1) * BKV;
-      const int n_valid = p.L - j * BKV;  // keys of this tile that exist
+      const int n_valid = p.L - (j_lo + j) * BKV;  // keys of this tile that exist
       const bool tail = n_valid < BKV;
       constexpr int NCH = BKV / 32;
       uint32_t r[NCH][32];   // the row's scores, read from TMEM exactly once
@@ -342,11 +385,11 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
           tmem_ld_wait();
           if (ch + 1 < NCH) tmem_ld_32x32b_x32(s_addr + 32 * (ch + 1), r[ch + 1]);
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            m0 = fmaxf(m0, __uint_as_float(r[ch][i]));
-            m1 = fmaxf(m1, __uint_as_float(r[ch][i + 1]));
-            m2 = fmaxf(m2, __uint_as_float(r[ch][i + 2]));
-            m3 = fmaxf(m3, __uint_as_float(r[ch][i + 3]));
+          for (int i = 0; i < 32; i += 8) {   // FMNMX3: two scores per instruction, four independent chains
+            m0 = fmax3(m0, __uint_as_float(r[ch][i]), __uint_as_float(r[ch][i + 1]));
+            m1 = fmax3(m1, __uint_as_float(r[ch][i + 2]), __uint_as_float(r[ch][i + 3]));
+            m2 = fmax3(m2, __uint_as_float(r[ch][i + 4]), __uint_as_float(r[ch][i + 5]));
+            m3 = fmax3(m3, __uint_as_float(r[ch][i + 6]), __uint_as_float(r[ch][i + 7]));
           }
           uint32_t pk[16];
           fa_exp32<false>(r[ch], pk, c, mc0, 32 * ch, n_valid, sum0, sum1);
@@ -392,31 +435,47 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full(j & 1));
     }
-    // ---- epilogue: O / l -> fp16 -> o[b, row, h*d : h*d + d]
     mbar_wait(o_ready((nkv - 1) & 1), ((nkv - 1) >> 1) & 1u);
     tc_fence_after();
-    const float inv = 1.f / l_run;
-    __half* orow = p.o + (static_cast<size_t>(b) * p.L + row) * p.C + h * p.d;
+    if (nparts == 1) {
+      // ---- epilogue: O / l -> fp16 -> o[b, row, h*d : h*d + d]
+      const float inv = 1.f / l_run;
+      __half* orow = p.o + (static_cast<size_t>(b) * p.L + row) * p.C + h * p.d;
 #pragma unroll
-    for (int cb = 0; cb < C::DV_N; cb += 16) {
-      uint32_t r[16];
-      tmem_ld_32x32b_x16(tmem_o + lane_field + cb, r);
-      tmem_ld_wait();
-      if (row < p.L) {
+      for (int cb = 0; cb < C::DV_N; cb += 16) {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(tmem_o + lane_field + cb, r);
+        tmem_ld_wait();
+        if (row < p.L) {
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          if (cb + g * 8 < p.d) {  // d % 8 == 0
-            uint4 v;
-            uint32_t* pv = reinterpret_cast<uint32_t*>(&v);
+          for (int g = 0; g < 2; ++g) {
+            if (cb + g * 8 < p.d) {  // d % 8 == 0
+              uint4 v;
+              uint32_t* pv = reinterpret_cast<uint32_t*>(&v);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const __half2 hh = __floats2half2_rn(__uint_as_float(r[g * 8 + 2 * e]) * inv,
-                                                   __uint_as_float(r[g * 8 + 2 * e + 1]) * inv);
-              pv[e] = *reinterpret_cast<const uint32_t*>(&hh);
+              for (int e = 0; e < 4; ++e) {
+                const __half2 hh = __floats2half2_rn(__uint_as_float(r[g * 8 + 2 * e]) * inv,
+                                                     __uint_as_float(r[g * 8 + 2 * e + 1]) * inv);
+                pv[e] = *reinterpret_cast<const uint32_t*>(&hh);
+              }
+              *reinterpret_cast<uint4*>(orow + cb + g * 8) = v;
             }
-            *reinterpret_cast<uint4*>(orow + cb + g * 8) = v;
           }
         }
+      }
+    } else {
+      // ---- split tile: un-normalised O, reference max and denominator of this key range
+      const size_t prow = (static_cast<size_t>(tile - p.n_full) * nparts + part) * BQ + quad * 32 + lane;
+      p.part_ml[prow] = make_float2(m_ref * c, l_run);
+      float* po = p.part_o + prow * C::DV_N;
+#pragma unroll
+      for (int cb = 0; cb < C::DV_N; cb += 16) {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(tmem_o + lane_field + cb, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          *reinterpret_cast<uint4*>(po + cb + 4 * g) = make_uint4(r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
       }
     }
   }
@@ -429,8 +488,55 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
   }
 }
 
+// Merge the key-range partials of the split tiles: with M = max_p m_p and w_p = 2^(m_p - M),
+//   o = sum_p w_p O_p / sum_p w_p l_p.   One thread per (row, 8 output columns).
+__global__ void fa_combine_kernel(const FaParams p, int dv_n, int n_split_tiles) {
+  const int groups = p.d / 8;
+  const long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (t >= static_cast<long long>(n_split_tiles) * BQ * groups) return;
+  const int g = static_cast<int>(t % groups);
+  const int r = static_cast<int>((t / groups) % BQ);
+  const int st = static_cast<int>(t / (static_cast<long long>(groups) * BQ));
+  const int tile = p.n_full + st;
+  const int row = (tile % p.n_qtiles) * BQ + r;
+  if (row >= p.L) return;
+  const int h = (tile / p.n_qtiles) % p.H;
+  const int b = tile / (p.n_qtiles * p.H);
+  const size_t prow0 = static_cast<size_t>(st) * p.splits * BQ + r;
+  float M = -INFINITY;
+  for (int s = 0; s < p.splits; ++s) M = fmaxf(M, p.part_ml[prow0 + static_cast<size_t>(s) * BQ].x);
+  float l = 0.f, acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int s = 0; s < p.splits; ++s) {
+    const size_t prow = prow0 + static_cast<size_t>(s) * BQ;
+    const float2 ml = p.part_ml[prow];
+    const float w = exp2f(ml.x - M);
+    l = fmaf(w, ml.y, l);
+    const float4* po = reinterpret_cast<const float4*>(p.part_o + prow * dv_n + g * 8);
+    const float4 a0 = po[0], a1 = po[1];
+    acc[0] = fmaf(w, a0.x, acc[0]); acc[1] = fmaf(w, a0.y, acc[1]);
+    acc[2] = fmaf(w, a0.z, acc[2]); acc[3] = fmaf(w, a0.w, acc[3]);
+    acc[4] = fmaf(w, a1.x, acc[4]); acc[5] = fmaf(w, a1.y, acc[5]);
+    acc[6] = fmaf(w, a1.z, acc[6]); acc[7] = fmaf(w, a1.w, acc[7]);
+  }
+  const float inv = 1.f / l;
+  uint4 v;
+  uint32_t* pv = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const __half2 hh = __floats2half2_rn(acc[2 * e] * inv, acc[2 * e + 1] * inv);
+    pv[e] = *reinterpret_cast<const uint32_t*>(&hh);
+  }
+  *reinterpret_cast<uint4*>(p.o + (static_cast<size_t>(b) * p.L + row) * p.C + h * p.d + g * 8) = v;
+}
+
+// Upper bound on split units (remainder tiles x splits); sizes the partial buffers in the workspace.
+constexpr int FA_MAX_SPLIT_UNITS = 320;
+constexpr int FA_MAX_SPLITS = 8;
+constexpr size_t FA_PART_BYTES = static_cast<size_t>(FA_MAX_SPLIT_UNITS) * BQ * (128 * sizeof(float) + sizeof(float2));
+
 template <int KSTEPS>
-int launch_fa(const void* qkvh, __half* o, int B, int L, int C, int H, int d, float scale, cudaStream_t stream) {
+int launch_fa(const void* qkvh, __half* o, void* part_ws, int B, int L, int C, int H, int d, float scale,
+              cudaStream_t stream) {
   using Cf = FaCfg<KSTEPS>;
   CUtensorMap tq, tk, tv;
   const int DP = Cf::ATOMS * 64;                       // padded head_dim of the head-major q/k/v buffers
@@ -446,12 +552,53 @@ int launch_fa(const void* qkvh, __half* o, int B, int L, int C, int H, int d, fl
   rc = cuda_rc(cudaFuncSetAttribute(flash_attn_kernel<KSTEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(Cf::SMEM_BYTES)));
   if (rc) return rc;
+  int sms = 0, per_sm = 0;
+  rc = gemm::device_sms(&sms);
+  if (rc) return rc;
+  rc = cuda_rc(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flash_attn_kernel<KSTEPS>, FA_THREADS,
+                                                             Cf::SMEM_BYTES));
+  if (rc) return rc;
+  const int slots = sms * (per_sm > 0 ? per_sm : 1);
+
   FaParams p;
   p.L = L; p.H = H; p.d = d; p.C = C;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.o = o;
-  dim3 grid((L + BQ - 1) / BQ, H, B);
-  flash_attn_kernel<KSTEPS><<<grid, FA_THREADS, Cf::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  p.n_qtiles = (L + BQ - 1) / BQ;
+  // Every tile costs the same, so the grid runs in waves of `slots` CTAs and the last, partial wave leaves most of
+  // the GPU idle for a whole tile time.  The tiles of that wave are cut into `splits` key ranges instead (chosen to
+  // minimise the time of the remainder, ceil(R * S / slots) / S tile times) and merged by fa_combine_kernel.
+  const long long tiles = static_cast<long long>(p.n_qtiles) * H * B;
+  const int nkv = (L + Cf::BKV - 1) / Cf::BKV;
+  const int rem = static_cast<int>(tiles % slots);
+  int splits = 1;
+  if (rem > 0) {
+    // Time of the remainder in tile times.  The kernel is bound by per-SM throughput (MUFU), so what counts is the
+    // number of units the busiest SM gets, not CTA slots: sub-waves over `sms` x (1 / S + fixed cost of a unit,
+    // about four key tiles).  Split only for a clear gain (the merge is one more launch).
+    const double fixed = 4.0 / nkv;
+    double best_t = 0.9;
+    for (int sp = 2; sp <= FA_MAX_SPLITS && sp * 4 <= nkv && rem * sp <= FA_MAX_SPLIT_UNITS; ++sp) {
+      const double t = static_cast<double>((static_cast<long long>(rem) * sp + sms - 1) / sms) * (1.0 / sp + fixed);
+      if (t < best_t - 1e-9) { best_t = t; splits = sp; }
+    }
+  }
+  if (const char* e = getenv("VTM_FA_SPLITS")) {   // tuning override (tools/sweep_fa_splits.py)
+    const int sp = atoi(e);
+    if (sp >= 1 && sp <= FA_MAX_SPLITS && sp <= nkv && static_cast<long long>(rem) * sp <= FA_MAX_SPLIT_UNITS)
+      splits = rem > 0 ? sp : 1;
+  }
+  p.splits = splits;
+  p.n_full = static_cast<int>(splits > 1 ? tiles - rem : tiles);
+  p.part_ml = static_cast<float2*>(part_ws);
+  p.part_o = reinterpret_cast<float*>(static_cast<char*>(part_ws) +
+                                      static_cast<size_t>(FA_MAX_SPLIT_UNITS) * BQ * sizeof(float2));
+  const long long units = p.n_full + (tiles - p.n_full) * splits;
+  flash_attn_kernel<KSTEPS><<<static_cast<unsigned>(units), FA_THREADS, Cf::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  rc = launch_rc();
+  if (rc || splits == 1) return rc;
+  const long long work = static_cast<long long>(rem) * BQ * (d / 8);
+  fa_combine_kernel<<<static_cast<unsigned>((work + 255) / 256), 256, 0, stream>>>(p, Cf::DV_N, rem);
   return launch_rc();
 }
 
@@ -464,8 +611,8 @@ extern "C" size_t vtm_attention_workspace_bytes(int32_t B, int32_t L, int32_t C,
   if (heads <= 0 || C % heads != 0) return 0;
   const int d = C / heads;
   const size_t DP = d <= 64 ? 64 : 128;
-  // q/k/v head-major [3][B][H][L][DP] + o [B*L, C], fp16
-  return (static_cast<size_t>(3) * B * heads * L * DP + static_cast<size_t>(B) * L * C) * 2;
+  // q/k/v head-major [3][B][H][L][DP] + o [B*L, C], fp16; then the key-range partials of the split tiles
+  return (static_cast<size_t>(3) * B * heads * L * DP + static_cast<size_t>(B) * L * C) * 2 + vtm::FA_PART_BYTES + 256;
 }
 
 extern "C" int vtm_attention(const void* x_dev, const void* w_qkv_dev, const void* w_o_dev, const void* b_o_dev,
@@ -483,15 +630,17 @@ extern "C" int vtm_attention(const void* x_dev, const void* w_qkv_dev, const voi
   __half* qkv = static_cast<__half*>(ws_dev);
   __half* o = qkv + static_cast<size_t>(3) * B * heads * L * DP;
   const int M = B * L;
+  void* part_ws = reinterpret_cast<void*>(
+      (reinterpret_cast<uintptr_t>(o + static_cast<size_t>(M) * C) + 255u) & ~static_cast<uintptr_t>(255u));
   int rc = launch_qkv_heads(x_dev, w_qkv_dev, qkv, B, L, C, heads, DP, stream);
   if (rc) return rc;
   const int ksteps = (d + 15) / 16;
   switch (ksteps) {
-    case 1: case 2: case 3: rc = launch_fa<3>(qkv, o, B, L, C, heads, d, scale, stream); break;
-    case 4: rc = launch_fa<4>(qkv, o, B, L, C, heads, d, scale, stream); break;
-    case 5: rc = launch_fa<5>(qkv, o, B, L, C, heads, d, scale, stream); break;
-    case 6: rc = launch_fa<6>(qkv, o, B, L, C, heads, d, scale, stream); break;
-    default: rc = launch_fa<8>(qkv, o, B, L, C, heads, d, scale, stream); break;
+    case 1: case 2: case 3: rc = launch_fa<3>(qkv, o, part_ws, B, L, C, heads, d, scale, stream); break;
+    case 4: rc = launch_fa<4>(qkv, o, part_ws, B, L, C, heads, d, scale, stream); break;
+    case 5: rc = launch_fa<5>(qkv, o, part_ws, B, L, C, heads, d, scale, stream); break;
+    case 6: rc = launch_fa<6>(qkv, o, part_ws, B, L, C, heads, d, scale, stream); break;
+    default: rc = launch_fa<8>(qkv, o, part_ws, B, L, C, heads, d, scale, stream); break;
   }
   if (rc) return rc;
   return vtm_linear_f16(o, w_o_dev, b_o_dev, M, C, C, y_dev, C, stream_);

@@ -16,21 +16,33 @@ struct Split {
   int mode, N, unm_pre, F, tnum, stride, randf, src_len;
   int nd_frames;  // local: number of dst frames = #{f in [0,F): f % stride == randf}
   int Ns, Nd;
+  const int32_t* randf_dev;  // device-resident randf (NULL = the value above); see resolve_split()
 };
+
+// Kernels call this first: with a device-resident draw, fetch it (the counts do not depend on it, make_split).
+__device__ __forceinline__ void resolve_split(Split& s) {
+  if (s.randf_dev) s.randf = __ldg(s.randf_dev);
+}
 
 __host__ inline int make_split(const vtm_split_t* s, Split* o) {
   if (!s) return VTM_E_NULL;
   o->mode = s->mode; o->N = s->N; o->unm_pre = s->unm_pre; o->F = s->F; o->tnum = s->tnum;
   o->stride = s->stride; o->randf = s->randf; o->src_len = s->src_len; o->nd_frames = 0;
+  o->randf_dev = s->mode == 0 ? s->randf_dev : nullptr;
   if (s->N <= 0) return VTM_E_SPLIT;
   if (s->mode == 0) {
-    if (s->F <= 0 || s->tnum <= 0 || s->stride <= 0 || s->stride > s->F || s->randf < 0 ||
-        s->randf >= s->stride || s->unm_pre < 0)
+    if (o->randf_dev) {
+      // the draw stays on the device: the counts below must not depend on it
+      if (s->stride <= 0 || s->F <= 0 || s->F % s->stride != 0) return VTM_E_SPLIT;
+      o->randf = 0;
+    }
+    if (s->F <= 0 || s->tnum <= 0 || s->stride <= 0 || s->stride > s->F || o->randf < 0 ||
+        o->randf >= s->stride || s->unm_pre < 0)
       return VTM_E_SPLIT;
     // merge.py:43 tnum = (N - unm_pre) // F; the index buffer covers all N - unm_pre positions and
     // the frame id is pos // tnum (merge.py:59), so N - unm_pre must be exactly F * tnum.
     if ((long long)s->F * s->tnum != (long long)s->N - s->unm_pre) return VTM_E_SPLIT;
-    o->nd_frames = (s->F - s->randf + s->stride - 1) / s->stride;
+    o->nd_frames = (s->F - o->randf + s->stride - 1) / s->stride;
     o->Nd = o->nd_frames * s->tnum + s->unm_pre;
     o->Ns = s->N - o->Nd;
   } else if (s->mode == 1) {

@@ -73,6 +73,51 @@ struct Work {
   }
 };
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Row-contiguous stores for epilogues that write the tile to global memory.  After tcgen05.ld a thread holds ONE
+// row of the tile, so a direct 16-byte store per thread touches 32 different cache lines per instruction (ncu:
+// L1TEX at 63 % of peak, the busiest unit of the projection GEMMs, and every sector written half at a time).  The
+// warp's 32 rows x 64 fp16 columns go through a 4 KB XOR-swizzled staging area instead: each thread writes its row
+// as eight 16-byte chunks (chunk k at slot k ^ (row & 7): conflict-free), then lane l reads chunk l & 7 of row
+// 4 i + l / 8, so that eight consecutive lanes store 128 contiguous bytes of one row.
+constexpr uint32_t STAGE_STORE_BYTES = 32 * 128;
+template <class F>
+__device__ __forceinline__ void warp_store_rows64(uint32_t scratch, const uint32_t (&pk)[32], F&& store) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(scratch + lane * 128 + ((k ^ (lane & 7)) << 4)),
+                 "r"(pk[4 * k]), "r"(pk[4 * k + 1]), "r"(pk[4 * k + 2]), "r"(pk[4 * k + 3])
+                 : "memory");
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = 4 * i + (lane >> 3), kk = lane & 7;
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"(scratch + r * 128 + ((kk ^ (r & 7)) << 4))
+                 : "memory");
+    store(r, kk * 8, v);   // row within the warp's 32, first of 8 columns within the 64
+  }
+  __syncwarp();
+}
+
+#if defined(VTM_EXP_TRACE)   // timing experiment (tools/ubench/gemm_trace.cu): per-CTA event times in ns
+__device__ unsigned long long vtm_trace[160][64];
+#define VTM_TRACE(slot)                                                                   \
+  do {                                                                                    \
+    if ((slot) < 64) {                                                                    \
+      unsigned long long t_;                                                              \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                              \
+      vtm_trace[blockIdx.x][(slot)] = t_;                                                 \
+    }                                                                                     \
+  } while (0)
+#else
+#define VTM_TRACE(slot) do { } while (0)
+#endif
+
 template <int BN, class Epi>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -92,6 +137,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) VTM_TRACE(0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -164,6 +210,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #if !defined(VTM_EXP_NO_FULL_WAIT)   // timing experiment: MMA does not wait for the loads
             mbar_wait(full_bar(stage), phase);
 #endif
+            if (kc == 0) VTM_TRACE(2 + 4 * tile_ctr);          // first operands of the tile have landed
             tc_fence_after();
             const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
             const uint64_t adesc = umma_desc_sw128_kmajor(sa);
@@ -177,6 +224,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
           umma_commit(tfull_bar(as));  // accumulator complete
+          VTM_TRACE(3 + 4 * tile_ctr);                          // all MMAs of the tile issued
         }
       }
     }
@@ -187,6 +235,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const int row_in_tile = quad * 32 + lane;
     uint32_t tile_ctr = 0;
     Epi e = epi;  // per-thread mutable copy of the policy (kernel parameters are read-only)
+    // optional per-warp staging area behind the barriers (epilogues that transpose through shared memory)
+    if constexpr (Epi::SCRATCH_PER_WARP > 0)
+      e.set_scratch(bar_base + 256u + static_cast<uint32_t>(warp - 2) * Epi::SCRATCH_PER_WARP);
     for (int w = blockIdx.x; w < wk.total; w += gridDim.x) {
       int m_tile, b, nt0, nt1;
       wk.decode(w, &m_tile, &b, &nt0, &nt1);
@@ -196,6 +247,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const uint32_t aphase = (tile_ctr >> 1) & 1u;
         mbar_wait(tfull_bar(as), aphase);
         tc_fence_after();
+        if (warp == 2 && lane == 0) VTM_TRACE(4 + 4 * tile_ctr);   // accumulator complete (MMAs retired)
         const uint32_t taddr =
             tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + half * (BN / 2);
 #if !defined(VTM_EXP_NO_EPI)   // timing experiment: accumulators are not read
@@ -205,6 +257,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(as));
+        if (warp == 2 && lane == 0) VTM_TRACE(5 + 4 * tile_ctr);   // epilogue of the tile done (this warp)
       }
       e.end(m_tile, b, row_in_tile);
     }
@@ -212,6 +265,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) VTM_TRACE(1);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -222,11 +276,12 @@ template <int BN, class Epi>
 inline int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Work& wk, const Epi& epi, int sms,
                   cudaStream_t stream) {
   using C = Cfg<BN>;
+  const size_t smem = C::SMEM_BYTES + static_cast<size_t>(EPI_WARPS) * Epi::SCRATCH_PER_WARP;
   int rc = cuda_rc(cudaFuncSetAttribute(gemm_kernel<BN, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(C::SMEM_BYTES)));
+                                        static_cast<int>(smem)));
   if (rc) return rc;
   const int grid = wk.total < sms ? wk.total : sms;
-  gemm_kernel<BN, Epi><<<grid, THREADS, C::SMEM_BYTES, stream>>>(ta, tb, wk, epi);
+  gemm_kernel<BN, Epi><<<grid, THREADS, smem, stream>>>(ta, tb, wk, epi);
   return launch_rc();
 }
 

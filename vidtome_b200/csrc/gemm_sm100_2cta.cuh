@@ -131,6 +131,7 @@ gemm_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int row_in_tile = quad * 32 + lane;
     uint32_t tile_ctr = 0;
     Epi e = epi;
+    static_assert(Epi::SCRATCH_PER_WARP == 0, "the CTA-pair mainloop has no epilogue staging area");
     for (int w = pair; w < wk.total; w += n_pairs) {
       int m_tile, b, nt0, nt1;
       wk.decode(w, &m_tile, &b, &nt0, &nt1);

@@ -8,44 +8,45 @@ namespace vtm {
 namespace {
 
 struct StoreEpi {
+  static constexpr uint32_t SCRATCH_PER_WARP = gemm::STAGE_STORE_BYTES;
   __half* d;
   const __half* bias;
   long long ldd;
   int M, N;
-  int row;
+  int row0;            // first of the warp's 32 rows
+  uint32_t scratch;
 
+  __device__ __forceinline__ void set_scratch(uint32_t a) { scratch = a; }
   __device__ __forceinline__ void begin(int m_tile, int, int row_in_tile) {
-    row = m_tile * gemm::BM + row_in_tile;
+    row0 = m_tile * gemm::BM + (row_in_tile & ~31);
   }
   __device__ __forceinline__ void tile(uint32_t taddr, int col0, int ncols) {
 #pragma unroll 1
-    for (int cb = 0; cb < ncols; cb += 32) {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(taddr + cb, r);
+    for (int cb = 0; cb < ncols; cb += 64) {
+      uint32_t r[64];
+      tmem_ld_32x32b_x64(taddr + cb, r);
       tmem_ld_wait();
-      if (row < M) {
-        __half* drow = d + static_cast<long long>(row) * ldd;
+      uint32_t pk[32];
+      const int c0 = col0 + cb;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {  // groups of 8 columns = one 16-byte store
-          const int c = col0 + cb + g * 8;
-          if (c < N) {                 // N % 8 == 0: a group is entirely inside or outside
-            uint4 v;
-            uint32_t* pv = reinterpret_cast<uint32_t*>(&v);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float f0 = __uint_as_float(r[g * 8 + 2 * e]);
-              float f1 = __uint_as_float(r[g * 8 + 2 * e + 1]);
-              if (bias) {
-                f0 += __half2float(bias[c + 2 * e]);
-                f1 += __half2float(bias[c + 2 * e + 1]);
-              }
-              const __half2 h = __floats2half2_rn(f0, f1);
-              pv[e] = *reinterpret_cast<const uint32_t*>(&h);
-            }
-            *reinterpret_cast<uint4*>(drow + c) = v;
-          }
+      for (int e = 0; e < 32; ++e) {
+        float f0 = __uint_as_float(r[2 * e]), f1 = __uint_as_float(r[2 * e + 1]);
+        if (bias && c0 + 2 * e < N) {          // N % 8 == 0
+          f0 += __half2float(bias[c0 + 2 * e]);
+          f1 += __half2float(bias[c0 + 2 * e + 1]);
         }
+        pk[e] = pack_f16x2(f0, f1);
       }
+      // store phase: this lane writes columns [c, c + 8) of rows row0 + lane / 8 + 4 i
+      const int c = c0 + (threadIdx.x & 7) * 8;
+      int row = row0 + ((threadIdx.x & 31) >> 3);
+      __half* dst = d + static_cast<long long>(row) * ldd + c;
+      const long long row_step = 4 * ldd;
+      gemm::warp_store_rows64(scratch, pk, [&](int, int, const uint4& v) {
+        if (row < M && c < N) *reinterpret_cast<uint4*>(dst) = v;
+        row += 4;
+        dst += row_step;
+      });
     }
   }
   __device__ __forceinline__ void end(int, int, int) {}
@@ -67,7 +68,7 @@ extern "C" int vtm_linear_f16(const void* a_dev, const void* w_dev, const void* 
   StoreEpi epi;
   epi.d = static_cast<__half*>(d_dev);
   epi.bias = static_cast<const __half*>(bias_dev);
-  epi.ldd = ldd; epi.M = M; epi.N = N; epi.row = 0;
+  epi.ldd = ldd; epi.M = M; epi.N = N; epi.row0 = 0; epi.scratch = 0;
   CUtensorMap ta, tb;
   rc = make_tmap_3d_f16(&ta, a_dev, K, M, 1, K, static_cast<uint64_t>(M) * K, gemm::BK, gemm::BM);
   if (rc) return rc;
@@ -77,11 +78,11 @@ extern "C" int vtm_linear_f16(const void* a_dev, const void* w_dev, const void* 
   if (wide) {
     rc = make_tmap_3d_f16(&tb, w_dev, K, N, 1, K, static_cast<uint64_t>(N) * K, gemm::BK, 256);
     if (rc) return rc;
-    wk.plan(M, N, K, 1, 256, sms, 4, 1);
+    wk.plan(M, N, K, 1, 256, sms, 16, 1);
     return gemm::launch<256, StoreEpi>(ta, tb, wk, epi, sms, stream);
   }
   rc = make_tmap_3d_f16(&tb, w_dev, K, N, 1, K, static_cast<uint64_t>(N) * K, gemm::BK, 128);
   if (rc) return rc;
-  wk.plan(M, N, K, 1, 128, sms, 4, 1);
+  wk.plan(M, N, K, 1, 128, sms, 16, 1);
   return gemm::launch<128, StoreEpi>(ta, tb, wk, epi, sms, stream);
 }

@@ -105,6 +105,7 @@ __global__ void __launch_bounds__(ROW_THREADS)
 normalize_split_kernel(const __half* __restrict__ x, long long x_bs, const int* __restrict__ rowmap,
                        long long map_bs, Split sp, int B, int C, LnParams ln, __half* __restrict__ a_out,
                        __half* __restrict__ b_out) {
+  resolve_split(sp);
   constexpr int RPW = 32 / G;                       // rows per warp
   const int lane = threadIdx.x & 31;
   const int sub = lane % G, grp = lane / G;

@@ -18,6 +18,7 @@ namespace {
 constexpr int BN = 256;
 
 struct ArgmaxEpi {
+  static constexpr uint32_t SCRATCH_PER_WARP = 0;
   unsigned long long* keys;  // [B', Ns]
   int Ns, Nd, align_batch;
   float best;          // running maximum of this work item, or the entry threshold while best_idx is "none"

@@ -137,6 +137,7 @@ compose_maps_kernel(Split sp, int r, int Bp, const unsigned long long* __restric
                     const int* __restrict__ edge, const int* __restrict__ rank, const int* __restrict__ mu_in,
                     const int* __restrict__ pi_in, int pi_offset, int N0, int* __restrict__ mu_out,
                     int* __restrict__ pi_out) {
+  resolve_split(sp);
   const int b = blockIdx.y;
   const int Ns = sp.Ns, Nd = sp.Nd;
   const int unm = Ns - r;

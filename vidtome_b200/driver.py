@@ -36,8 +36,22 @@ class ChunkedDenoiser:
 
     def __init__(self, unet: torch.nn.Module, n_timesteps: int = 50, chunk_size: int = 16,
                  guidance_scale: float = 7.5, merge_global: bool = False, chunk_ord: str = "seq",
-                 perm_div: int = 4, randomize_chunks: bool = False, cond: Optional[torch.Tensor] = None):
+                 perm_div: int = 4, randomize_chunks: bool = False, cond: Optional[torch.Tensor] = None,
+                 cuda_graph: bool = False, graph_warmup: int = 2):
+        """`cuda_graph=True`: after `graph_warmup` eager steps, the noise prediction of a whole step (every chunk:
+        CFG batch, UNet forward with the merge path, guidance combine) is captured once into a CUDA graph and
+        replayed; per step the host then issues one graph launch plus the DDIM update instead of ~250 kernel
+        launches.  The frame draws of the local matcher stay on the device (utils.draw_randf) and come from the
+        blocks' generators, which are registered with the graph, so replays produce the same sequence of draws —
+        and bit-identical latents — as eager stepping.  Needs static shapes and chunk order: local merging only
+        (`merge_global=False`), `randomize_chunks=False`, frame counts divisible by the target stride."""
         self.unet = unet
+        self.cuda_graph = bool(cuda_graph)
+        self.graph_warmup = int(graph_warmup)
+        self._graph = None          # (CUDAGraph, static x, static timestep, static noise, shape)
+        self._eager_steps = 0
+        if self.cuda_graph and (merge_global or randomize_chunks):
+            raise ValueError("cuda_graph=True needs merge_global=False and randomize_chunks=False (static work)")
         self.chunk_size = chunk_size
         self.guidance_scale = guidance_scale
         self.merge_global = merge_global
@@ -97,15 +111,53 @@ class ChunkedDenoiser:
         pred_x0 = (x - sigma * eps) / mu
         return mu_prev * pred_x0 + sigma_prev * eps
 
-    # one iteration of generate.py:211-224
-    @torch.no_grad()
-    def step(self, x: torch.Tensor, i: int) -> torch.Tensor:
+    def _all_noises(self, x: torch.Tensor, t) -> torch.Tensor:
         noises = torch.zeros_like(x)
         for chunk in self.get_chunks(len(x)):
             # chunks are contiguous frame ranges (possibly visited in another order): slice instead of indexing with
             # a host tensor, which would cost a synchronous host->device copy per chunk per step
             lo, hi = int(chunk[0]), int(chunk[-1]) + 1
-            noises[lo:hi] = self.pred_noise(x[lo:hi], self.timesteps[i])
+            noises[lo:hi] = self.pred_noise(x[lo:hi], t)
+        return noises
+
+    def _block_generators(self) -> List[torch.Generator]:
+        seen, gens = set(), []
+        for m in self.unet.modules():
+            g = getattr(m, "generator", None)
+            if isinstance(g, torch.Generator) and g.device.type == "cuda" and id(g) not in seen:
+                seen.add(id(g))
+                gens.append(g)
+        return gens
+
+    def _capture(self, x: torch.Tensor, t: int):
+        """Capture `_all_noises` for inputs shaped like `x` (called after the eager warm-up steps, so that every
+        lazily created piece of state — generators forked by the hook, cached packed weights, the library handle,
+        allocator pools — already exists)."""
+        gx = x.clone()
+        gt = torch.tensor(int(t), device=x.device, dtype=torch.long)      # the UNet's timestep input, set per replay
+        graph = torch.cuda.CUDAGraph()
+        for g in self._block_generators():
+            graph.register_generator_state(g)
+        torch.cuda.synchronize(x.device)
+        with torch.cuda.graph(graph):
+            gn = self._all_noises(gx, gt)
+        self._graph = (graph, gx, gt, gn, tuple(x.shape))
+
+    # one iteration of generate.py:211-224
+    @torch.no_grad()
+    def step(self, x: torch.Tensor, i: int) -> torch.Tensor:
+        t = self.timesteps[i]
+        if self.cuda_graph and x.is_cuda and self._eager_steps >= self.graph_warmup:
+            if self._graph is None or self._graph[4] != tuple(x.shape):
+                self._capture(x, t)
+            graph, gx, gt, gn, _ = self._graph
+            gx.copy_(x, non_blocking=True)
+            gt.fill_(int(t))
+            graph.replay()
+            noises = gn
+        else:
+            self._eager_steps += 1
+            noises = self._all_noises(x, t)
         x = self.pred_next_x(x, noises, i)
         if self.merge_global:
             patch.update_patch(self.unet, global_tokens=None)                # generate.py:233-236

@@ -20,7 +20,7 @@ import torch
 
 from . import ops
 from ._lib import VtmSplit
-from .utils import draw_scalar
+from .utils import draw_randf
 
 
 def do_nothing(x: torch.Tensor, mode: str = None, **kwarg):
@@ -121,8 +121,7 @@ def bipartite_soft_matching_randframe(metric: torch.Tensor, F: int, ratio: float
         return do_nothing, do_nothing, {"unm_num": tnum}         # merge.py:45-46
     _check_metric(metric)
     stride = min(target_stride, F)                               # merge.py:55
-    randf = int(draw_scalar(generator, lambda: torch.randint(
-        0, stride, torch.Size([1]), generator=generator, device=generator.device)))  # merge.py:56-57 (same draw)
+    randf = draw_randf(generator, stride, F)                     # merge.py:56-57 (same draw)
     split = VtmSplit.local(N, unm_pre, F, target_stride, randf)
     m = match_level(metric.contiguous(), None, split, ratio, align_batch)
     merge, unmerge = _closures(m, N, None, merge_mode)

@@ -22,7 +22,7 @@ import torch
 
 from . import merge, ops
 from ._lib import VtmSplit
-from .utils import (draw_scalar, func_warper, init_generator, isinstance_str, join_frame, join_warper,
+from .utils import (draw_randf, draw_scalar, func_warper, init_generator, isinstance_str, join_frame, join_warper,
                     split_frame, split_warper)
 
 
@@ -34,7 +34,7 @@ class MergePlan:
     merged_tokens: torch.Tensor           # [B, L, C] fp16, input of attn1
     pi: torch.Tensor                      # [B'|1, N0] int32: out[b, p] = y[b, pi[b, p]]
     levels: List[merge.LevelMatch] = field(default_factory=list)
-    randf: List[int] = field(default_factory=list)
+    randf: List[Any] = field(default_factory=list)      # ints (eager) or 1-element int32 CUDA tensors (graph capture)
     coin: Optional[float] = None
 
     def unmerge(self, y: torch.Tensor, **kwarg) -> torch.Tensor:
@@ -99,8 +99,7 @@ def build_merge_plan(module: torch.nn.Module, x: torch.Tensor, tome_info: Dict[s
             unm += (L - unm) // curF                                         # merge.py:45-46 (no draw)
         else:
             stride = min(args["target_stride"], curF)                        # merge.py:55
-            randf = int(draw_scalar(generator, lambda: torch.randint(
-                0, stride, torch.Size([1]), generator=generator, device=generator.device)))  # merge.py:56-57
+            randf = draw_randf(generator, stride, curF)                      # merge.py:56-57
             randfs.append(randf)
             split = VtmSplit.local(L, unm, curF, args["target_stride"], randf)
             m = merge.match_level(table, mu, split, ratio, align, ln)        # patch.py:45-46

@@ -72,3 +72,21 @@ def draw_scalar(generator: torch.Generator, fn):
         st = _rng_streams[dev] = torch.cuda.Stream(device=dev)
     with torch.cuda.stream(st):
         return fn().item()
+
+
+def draw_randf(generator: torch.Generator, stride: int, frames: int):
+    """The `torch.randint(0, stride, [1])` of vidtome/merge.py:56-57 (which frame of every `stride` is dst).
+    Eagerly: the Python int (read back through the side stream of draw_scalar).  While the current stream is being
+    captured into a CUDA graph nothing can be read back, so the draw stays on the device as a 1-element int32
+    tensor that the kernels dereference (vtm_split_t.randf_dev); each replay then draws a fresh value from the
+    generator, which must be registered with the graph.  That needs src / dst counts that do not depend on the
+    draw, i.e. frames % stride == 0."""
+    def fn():
+        return torch.randint(0, stride, torch.Size([1]), generator=generator, device=generator.device)
+    if generator.device.type == "cuda" and torch.cuda.is_current_stream_capturing():
+        if frames % stride != 0:
+            raise RuntimeError(f"CUDA-graph capture needs a frame count divisible by the target stride "
+                               f"(got {frames} frames, stride {stride}): token counts would depend on the draw")
+        return fn().to(torch.int32)
+    return int(draw_scalar(generator, fn))
+
