@@ -101,7 +101,7 @@ __device__ __forceinline__ void layer_norm_row(uint4 (&v)[P], int sub, int vecs,
 // torch half semantics: norm accumulates in fp32 and is rounded to fp16; the division is carried out
 // in fp32 on the fp16-rounded norm and rounded to fp16.
 template <int G, int P>
-__global__ void __launch_bounds__(ROW_THREADS)
+__global__ void __launch_bounds__(ROW_THREADS, 4)
 normalize_split_kernel(const __half* __restrict__ x, long long x_bs, const int* __restrict__ rowmap,
                        long long map_bs, Split sp, int B, int C, LnParams ln, __half* __restrict__ a_out,
                        __half* __restrict__ b_out) {
@@ -185,7 +185,7 @@ normalize_split_kernel(const __half* __restrict__ x, long long x_bs, const int* 
 // ------------------------------------------------------------------ KC / KE: row gathers
 // y[b, i, :] = [LN](x[b, map[b, i], :]) (+ resid[b, i, :]).
 template <int G, int P, bool ADD>
-__global__ void __launch_bounds__(ROW_THREADS)
+__global__ void __launch_bounds__(ROW_THREADS, 4)
 gather_rows_kernel(const __half* __restrict__ x, long long x_bs, const int* __restrict__ map, long long map_bs,
                    const __half* __restrict__ resid, int B, int L, int C, LnParams ln, __half* __restrict__ y,
                    long long y_bs) {
@@ -247,10 +247,19 @@ int sm_count(int* sms) {
   return cuda_rc(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev));
 }
 
-int grid_for_rows(long long rows, int rows_per_warp, int sms) {
+// Grid of a grid-stride row kernel: never more CTAs than are resident at once (sms x the kernel's occupancy), so
+// that all warps run the same number of iterations (+-1) instead of a short last wave.
+template <class K>
+int grid_for_rows(K kernel, long long rows, int rows_per_warp, int sms) {
+  static int per_sm = 0;        // one instance per kernel instantiation
+  if (per_sm == 0) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, ROW_THREADS, 0) != cudaSuccess || n < 1) n = 2;
+    per_sm = n;
+  }
   const long long warps = (rows + rows_per_warp - 1) / rows_per_warp;
   long long blocks = (warps + (ROW_THREADS / 32) - 1) / (ROW_THREADS / 32);
-  const long long cap = static_cast<long long>(sms) * 8;   // 8 CTAs of 256 threads per SM
+  const long long cap = static_cast<long long>(sms) * per_sm;
   if (blocks < 1) blocks = 1;
   if (blocks > cap) blocks = cap;
   return static_cast<int>(blocks);
@@ -284,7 +293,7 @@ extern "C" int vtm_normalize_split_ln(const void* x_dev, int64_t x_batch_stride,
   LnParams ln{static_cast<const __half*>(ln_weight_dev), static_cast<const __half*>(ln_bias_dev), ln_eps};
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
 #define CALL(G, P)                                                                                          \
-  normalize_split_kernel<G, P><<<grid_for_rows(rows, 32 / G, sms), ROW_THREADS, 0, st>>>(                   \
+  normalize_split_kernel<G, P><<<grid_for_rows(normalize_split_kernel<G, P>, rows, 32 / G, sms), ROW_THREADS, 0, st>>>(                   \
       static_cast<const __half*>(x_dev), x_batch_stride, rowmap_dev, rowmap_batch_stride, sp, B, C, ln,     \
       static_cast<__half*>(a_out_dev), static_cast<__half*>(b_out_dev));
   VTM_DISPATCH_GP(vecs, CALL)
@@ -315,7 +324,7 @@ extern "C" int vtm_gather_rows_ln(const void* x_dev, int64_t x_batch_stride, con
   LnParams ln{static_cast<const __half*>(ln_weight_dev), static_cast<const __half*>(ln_bias_dev), ln_eps};
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
 #define CALL(G, P)                                                                                       \
-  gather_rows_kernel<G, P, false><<<grid_for_rows(rows, 32 / G, sms), ROW_THREADS, 0, st>>>(             \
+  gather_rows_kernel<G, P, false><<<grid_for_rows(gather_rows_kernel<G, P, false>, rows, 32 / G, sms), ROW_THREADS, 0, st>>>(             \
       static_cast<const __half*>(x_dev), x_batch_stride, map_dev, map_batch_stride, nullptr, B, L, C, ln, \
       static_cast<__half*>(y_dev), y_batch_stride);
   VTM_DISPATCH_GP(vecs, CALL)
@@ -347,14 +356,14 @@ extern "C" int vtm_unmerge_add(const void* y_dev, int64_t y_batch_stride, const 
   LnParams ln{nullptr, nullptr, 0.f};
   if (resid_dev) {
 #define CALL(G, P)                                                                                          \
-  gather_rows_kernel<G, P, true><<<grid_for_rows(rows, 32 / G, sms), ROW_THREADS, 0, st>>>(                 \
+  gather_rows_kernel<G, P, true><<<grid_for_rows(gather_rows_kernel<G, P, true>, rows, 32 / G, sms), ROW_THREADS, 0, st>>>(                 \
       static_cast<const __half*>(y_dev), y_batch_stride, map_dev, map_batch_stride,                         \
       static_cast<const __half*>(resid_dev), B, N, C, ln, static_cast<__half*>(out_dev), out_bs);
     VTM_DISPATCH_GP(vecs, CALL)
 #undef CALL
   } else {
 #define CALL(G, P)                                                                                          \
-  gather_rows_kernel<G, P, false><<<grid_for_rows(rows, 32 / G, sms), ROW_THREADS, 0, st>>>(                \
+  gather_rows_kernel<G, P, false><<<grid_for_rows(gather_rows_kernel<G, P, false>, rows, 32 / G, sms), ROW_THREADS, 0, st>>>(                \
       static_cast<const __half*>(y_dev), y_batch_stride, map_dev, map_batch_stride, nullptr, B, N, C, ln,   \
       static_cast<__half*>(out_dev), out_bs);
     VTM_DISPATCH_GP(vecs, CALL)
