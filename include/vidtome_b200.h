@@ -173,6 +173,18 @@ int vtm_gather_rows(const void* x_dev, int64_t x_batch_stride, const int32_t* ma
                     int64_t map_batch_stride, int32_t B, int32_t L, int32_t C, void* y_dev,
                     int64_t y_batch_stride, void* stream);
 
+/*
+ * KC as the producer of the global-token exchange (the all-gather variant of vidtome/patch.py:59-82
+ * sharded one chunk per GPU): same as vtm_gather_rows_ln, and every output row is ALSO stored to n_peers (<= 8)
+ * further destinations `peer_y_devs[i]` — buffers of the same layout in other GPUs' memory, peer-mapped into this
+ * process (NVLink P2P; e.g. torch symmetric memory).  The merged tokens reach all ranks in the pass that creates
+ * them; the caller only adds a barrier before reading the peers' contributions.  peer_y_devs is a HOST array.
+ */
+int vtm_gather_rows_peers(const void* x_dev, int64_t x_batch_stride, const int32_t* map_dev,
+                          int64_t map_batch_stride, int32_t B, int32_t L, int32_t C, const void* ln_weight_dev,
+                          const void* ln_bias_dev, float ln_eps, void* y_dev, int64_t y_batch_stride,
+                          void* const* peer_y_devs, int32_t n_peers, void* stream);
+
 /* KC with norm1 fused: y[b, i, :] = LayerNorm(x[b, map[b, i], :]) — the merged tokens that feed attn1,
  * computed from the raw hidden states (only the L kept rows are ever normalised). */
 int vtm_gather_rows_ln(const void* x_dev, int64_t x_batch_stride, const int32_t* map_dev,

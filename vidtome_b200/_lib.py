@@ -51,6 +51,8 @@ SIGNATURES = {
     "vtm_normalize_split": (C.c_int, [_vp, _i64, _vp, _i64, _SPL, _i32, _i32, _vp, _vp, _vp]),
     "vtm_normalize_split_ln": (C.c_int, [_vp, _i64, _vp, _i64, _SPL, _i32, _i32, _vp, _vp, C.c_float, _vp, _vp, _vp]),
     "vtm_gather_rows_ln": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _vp, C.c_float, _vp, _i64, _vp]),
+    "vtm_gather_rows_peers": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _vp, C.c_float, _vp, _i64,
+                                        C.POINTER(C.c_void_p), _i32, _vp]),
     "vtm_sim_argmax": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "vtm_sim_argmax_simt": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "vtm_key_score_half_bits": (C.c_uint16, [C.c_uint64]),

@@ -184,11 +184,20 @@ normalize_split_kernel(const __half* __restrict__ x, long long x_bs, const int* 
 
 // ------------------------------------------------------------------ KC / KE: row gathers
 // y[b, i, :] = [LN](x[b, map[b, i], :]) (+ resid[b, i, :]).
+// KC can also be the producer side of the global-token exchange: `peers` lists further copies of y in OTHER GPUs'
+// memory (peer-mapped over NVLink), written by the same stores — the all-gather of the merged tokens then needs no
+// separate pass over them (vtm_gather_rows_peers).
+constexpr int MAX_PEERS = 8;
+struct PeerDsts {
+  __half* p[MAX_PEERS];
+  int n;
+};
+
 template <int G, int P, bool ADD>
 __global__ void __launch_bounds__(ROW_THREADS, 4)
 gather_rows_kernel(const __half* __restrict__ x, long long x_bs, const int* __restrict__ map, long long map_bs,
                    const __half* __restrict__ resid, int B, int L, int C, LnParams ln, __half* __restrict__ y,
-                   long long y_bs) {
+                   long long y_bs, PeerDsts peers) {
   constexpr int RPW = 32 / G;
   const int lane = threadIdx.x & 31;
   const int sub = lane % G, grp = lane / G;
@@ -235,6 +244,10 @@ gather_rows_kernel(const __half* __restrict__ x, long long x_bs, const int* __re
           for (int e = 0; e < 4; ++e) a[e] = __hadd2(a[e], r2[e]);
         }
         st_16(dst + (sub + G * i) * 8, v[i]);
+        if (!ADD) {
+          const long long off = (dst - y) + (sub + G * i) * 8;
+          for (int d = 0; d < peers.n; ++d) *reinterpret_cast<uint4*>(peers.p[d] + off) = v[i];
+        }
       }
     }
   }
@@ -293,9 +306,10 @@ extern "C" int vtm_normalize_split_ln(const void* x_dev, int64_t x_batch_stride,
   LnParams ln{static_cast<const __half*>(ln_weight_dev), static_cast<const __half*>(ln_bias_dev), ln_eps};
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
 #define CALL(G, P)                                                                                          \
-  normalize_split_kernel<G, P><<<grid_for_rows(normalize_split_kernel<G, P>, rows, 32 / G, sms), ROW_THREADS, 0, st>>>(                   \
-      static_cast<const __half*>(x_dev), x_batch_stride, rowmap_dev, rowmap_batch_stride, sp, B, C, ln,     \
-      static_cast<__half*>(a_out_dev), static_cast<__half*>(b_out_dev));
+  normalize_split_kernel<G, P>                                                                              \
+      <<<grid_for_rows(normalize_split_kernel<G, P>, rows, 32 / G, sms), ROW_THREADS, 0, st>>>(             \
+          static_cast<const __half*>(x_dev), x_batch_stride, rowmap_dev, rowmap_batch_stride, sp, B, C, ln, \
+          static_cast<__half*>(a_out_dev), static_cast<__half*>(b_out_dev));
   VTM_DISPATCH_GP(vecs, CALL)
 #undef CALL
   return launch_rc();
@@ -308,14 +322,21 @@ extern "C" int vtm_normalize_split(const void* x_dev, int64_t x_batch_stride, co
                                 nullptr, 0.f, a_out_dev, b_out_dev, stream_);
 }
 
-extern "C" int vtm_gather_rows_ln(const void* x_dev, int64_t x_batch_stride, const int32_t* map_dev,
-                                  int64_t map_batch_stride, int32_t B, int32_t L, int32_t C,
-                                  const void* ln_weight_dev, const void* ln_bias_dev, float ln_eps, void* y_dev,
-                                  int64_t y_batch_stride, void* stream_) {
+extern "C" int vtm_gather_rows_peers(const void* x_dev, int64_t x_batch_stride, const int32_t* map_dev,
+                                     int64_t map_batch_stride, int32_t B, int32_t L, int32_t C,
+                                     const void* ln_weight_dev, const void* ln_bias_dev, float ln_eps, void* y_dev,
+                                     int64_t y_batch_stride, void* const* peer_y_devs, int32_t n_peers,
+                                     void* stream_) {
   using namespace vtm;
-  if (!x_dev || !y_dev) return VTM_E_NULL;
+  if (!x_dev || !y_dev || (n_peers > 0 && !peer_y_devs)) return VTM_E_NULL;
   if (B <= 0 || L < 0 || C <= 0 || (C % 8) != 0 || C > 32 * 8 * 8) return VTM_E_SHAPE;
+  if (n_peers < 0 || n_peers > MAX_PEERS) return VTM_E_SHAPE;
   if (L == 0) return VTM_OK;
+  PeerDsts peers;
+  peers.n = n_peers;
+  for (int d = 0; d < MAX_PEERS; ++d) peers.p[d] = d < n_peers ? static_cast<__half*>(peer_y_devs[d]) : nullptr;
+  for (int d = 0; d < n_peers; ++d)
+    if (!peers.p[d]) return VTM_E_NULL;
   int sms = 0;
   int rc = sm_count(&sms);
   if (rc) return rc;
@@ -323,13 +344,22 @@ extern "C" int vtm_gather_rows_ln(const void* x_dev, int64_t x_batch_stride, con
   const int vecs = C / 8;
   LnParams ln{static_cast<const __half*>(ln_weight_dev), static_cast<const __half*>(ln_bias_dev), ln_eps};
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
-#define CALL(G, P)                                                                                       \
-  gather_rows_kernel<G, P, false><<<grid_for_rows(gather_rows_kernel<G, P, false>, rows, 32 / G, sms), ROW_THREADS, 0, st>>>(             \
-      static_cast<const __half*>(x_dev), x_batch_stride, map_dev, map_batch_stride, nullptr, B, L, C, ln, \
-      static_cast<__half*>(y_dev), y_batch_stride);
+#define CALL(G, P)                                                                                             \
+  gather_rows_kernel<G, P, false>                                                                              \
+      <<<grid_for_rows(gather_rows_kernel<G, P, false>, rows, 32 / G, sms), ROW_THREADS, 0, st>>>(             \
+          static_cast<const __half*>(x_dev), x_batch_stride, map_dev, map_batch_stride, nullptr, B, L, C, ln,  \
+          static_cast<__half*>(y_dev), y_batch_stride, peers);
   VTM_DISPATCH_GP(vecs, CALL)
 #undef CALL
   return launch_rc();
+}
+
+extern "C" int vtm_gather_rows_ln(const void* x_dev, int64_t x_batch_stride, const int32_t* map_dev,
+                                  int64_t map_batch_stride, int32_t B, int32_t L, int32_t C,
+                                  const void* ln_weight_dev, const void* ln_bias_dev, float ln_eps, void* y_dev,
+                                  int64_t y_batch_stride, void* stream_) {
+  return vtm_gather_rows_peers(x_dev, x_batch_stride, map_dev, map_batch_stride, B, L, C, ln_weight_dev, ln_bias_dev,
+                               ln_eps, y_dev, y_batch_stride, nullptr, 0, stream_);
 }
 
 extern "C" int vtm_gather_rows(const void* x_dev, int64_t x_batch_stride, const int32_t* map_dev,
@@ -356,16 +386,18 @@ extern "C" int vtm_unmerge_add(const void* y_dev, int64_t y_batch_stride, const 
   LnParams ln{nullptr, nullptr, 0.f};
   if (resid_dev) {
 #define CALL(G, P)                                                                                          \
-  gather_rows_kernel<G, P, true><<<grid_for_rows(gather_rows_kernel<G, P, true>, rows, 32 / G, sms), ROW_THREADS, 0, st>>>(                 \
-      static_cast<const __half*>(y_dev), y_batch_stride, map_dev, map_batch_stride,                         \
-      static_cast<const __half*>(resid_dev), B, N, C, ln, static_cast<__half*>(out_dev), out_bs);
+  gather_rows_kernel<G, P, true>                                                                            \
+      <<<grid_for_rows(gather_rows_kernel<G, P, true>, rows, 32 / G, sms), ROW_THREADS, 0, st>>>(           \
+          static_cast<const __half*>(y_dev), y_batch_stride, map_dev, map_batch_stride,                     \
+          static_cast<const __half*>(resid_dev), B, N, C, ln, static_cast<__half*>(out_dev), out_bs, PeerDsts{});
     VTM_DISPATCH_GP(vecs, CALL)
 #undef CALL
   } else {
 #define CALL(G, P)                                                                                          \
-  gather_rows_kernel<G, P, false><<<grid_for_rows(gather_rows_kernel<G, P, false>, rows, 32 / G, sms), ROW_THREADS, 0, st>>>(                \
-      static_cast<const __half*>(y_dev), y_batch_stride, map_dev, map_batch_stride, nullptr, B, N, C, ln,   \
-      static_cast<__half*>(out_dev), out_bs);
+  gather_rows_kernel<G, P, false>                                                                           \
+      <<<grid_for_rows(gather_rows_kernel<G, P, false>, rows, 32 / G, sms), ROW_THREADS, 0, st>>>(          \
+          static_cast<const __half*>(y_dev), y_batch_stride, map_dev, map_batch_stride, nullptr, B, N, C, ln, \
+          static_cast<__half*>(out_dev), out_bs, PeerDsts{});
     VTM_DISPATCH_GP(vecs, CALL)
 #undef CALL
   }

@@ -73,3 +73,61 @@ def exchange_global_tokens(local_tokens: torch.Tensor, group=None) -> Optional[t
         return None
     gathered = all_gather_tokens(local_tokens, group=group)
     return gathered[(rank() - 1) % w].contiguous()
+
+
+# ------------------------------------------------------------------ exchange fused into the producing kernel
+class PeerExchange:
+    """Global-token exchange without a collective pass: every rank owns a symmetric buffer `[2, world, B, L, C]`
+    (torch symmetric memory: peer-mapped over NVLink), and the KC kernel that creates a rank's merged tokens stores
+    each row into slot `rank` of EVERY rank's buffer (vtm_gather_rows_peers).  One barrier later all slots are
+    readable locally.  Two buffers alternate so that a rank may already write block l+1 while a peer still reads
+    block l (a rank can only reach its second-next write after passing the barrier in between, which every peer
+    enters after its reads of the older buffer are enqueued).
+
+    Same token length L on every rank is part of the contract (fixed chunking); it is verified once per shape."""
+
+    _cache = {}
+
+    def __init__(self, B: int, L: int, C: int, device: torch.device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.w, self.r = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if self.w - 1 > 8:
+            raise RuntimeError("PeerExchange: at most 9 ranks (8 peer destinations per store)")
+        lens = [None] * self.w
+        dist.all_gather_object(lens, (B, L, C), group=self.group)
+        if any(t != (B, L, C) for t in lens):
+            raise RuntimeError(f"PeerExchange needs identical token shapes on every rank, got {lens}")
+        self.shape = (B, L, C)
+        self.buf = symm.empty((2, self.w, B, L, C), dtype=torch.float16, device=device)
+        self.hdl = symm.rendezvous(self.buf, self.group)
+        self.phase = 0
+        self.slot_elems = B * L * C
+
+    @classmethod
+    def get(cls, B: int, L: int, C: int, device: torch.device, group=None) -> "PeerExchange":
+        key = (B, L, C, device.index, id(group))
+        ex = cls._cache.get(key)
+        if ex is None:
+            ex = cls._cache[key] = cls(B, L, C, device, group)
+        return ex
+
+    def produce(self, table: torch.Tensor, mu: torch.Tensor, ln=None):
+        """Run KC for this rank's tokens into slot `rank` everywhere; returns (local tokens, tokens of rank-1)."""
+        from . import ops
+        ph = self.phase
+        self.phase ^= 1
+        mine = self.buf[ph, self.r]
+        off = ((ph * self.w + self.r) * self.slot_elems) * 2                  # bytes from a buffer's base
+        peers = [int(self.hdl.buffer_ptrs[p]) + off for p in range(self.w) if p != self.r]
+        ops.gather_rows_peers(table, mu, mine, peers, ln=ln)
+        self.hdl.barrier(channel=ph)            # all ranks' stores of this block have landed
+        return mine, self.buf[ph, (self.r - 1) % self.w]
+
+
+def exchange_fused(table: torch.Tensor, mu: torch.Tensor, ln=None, group=None):
+    """KC + exchange in one kernel (`patch.GLOBAL_EXCHANGE = "p2p"`): (local merged tokens, tokens of rank k-1)."""
+    B, L, C = table.shape[0], mu.shape[1], table.shape[2]
+    ex = PeerExchange.get(B, L, C, table.device, group)
+    return ex.produce(table, mu, ln=ln)
+

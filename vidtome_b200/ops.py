@@ -6,7 +6,7 @@ tensors and raises on anything else — there is no CPU or eager-PyTorch impleme
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional, Tuple
+from typing import Sequence, Optional, Tuple
 
 import torch
 
@@ -181,6 +181,29 @@ def gather_rows(x: torch.Tensor, row_map: Optional[torch.Tensor], L: Optional[in
     lw, lb, eps = _ln_args(ln)
     check(_lib.load().vtm_gather_rows_ln(x.data_ptr(), x.stride(0), _ptr(row_map), map_bs, B, L, Cc, lw, lb, eps,
                                          out.data_ptr(), out.stride(0), _stream()), "vtm_gather_rows_ln")
+    STATS.launches += 1
+    return out
+
+
+def gather_rows_peers(x: torch.Tensor, row_map: Optional[torch.Tensor], out: torch.Tensor, peer_ptrs: Sequence[int],
+                      ln=None) -> torch.Tensor:
+    """KC + exchange: like gather_rows into `out` [B, L, C], and the same rows are stored to the buffers at
+    `peer_ptrs` (device addresses of identically laid out [B, L, C] regions in other GPUs' memory)."""
+    _require(x, torch.float16, "x")
+    _require(out, torch.float16, "out")
+    B, _, Cc = x.shape
+    L = out.shape[1]
+    map_bs = 0
+    if row_map is not None:
+        _require(row_map, torch.int32, "map")
+        if row_map.shape[1] != L:
+            raise RuntimeError("gather_rows_peers: map length != out length")
+        map_bs = 0 if row_map.shape[0] == 1 else L
+    arr = (C.c_void_p * max(1, len(peer_ptrs)))(*[C.c_void_p(int(q)) for q in peer_ptrs])
+    lw, lb, eps = _ln_args(ln)
+    check(_lib.load().vtm_gather_rows_peers(x.data_ptr(), x.stride(0), _ptr(row_map), map_bs, B, L, Cc, lw, lb, eps,
+                                            out.data_ptr(), out.stride(0), arr, len(peer_ptrs), _stream()),
+          "vtm_gather_rows_peers")
     STATS.launches += 1
     return out
 

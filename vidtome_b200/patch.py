@@ -114,14 +114,21 @@ def build_merge_plan(module: torch.nn.Module, x: torch.Tensor, tome_info: Dict[s
         pi = mu
     coin = None
     if args["merge_global"]:                                                 # patch.py:59
-        local_tokens = ops.gather_rows(table, mu, ln=ln)                     # merged local tokens [B, L, C]
         g = getattr(module, "global_tokens", None)
         exchanged = False
-        if GLOBAL_EXCHANGE == "allgather":
+        local_tokens = None
+        if GLOBAL_EXCHANGE in ("allgather", "p2p"):
             from . import dist as _dist
             if _dist.world() > 1:
-                g = _dist.exchange_global_tokens(local_tokens)              # the one collective of this path
+                if GLOBAL_EXCHANGE == "p2p":
+                    # KC stores the merged tokens into every rank's symmetric buffer: no separate collective pass
+                    local_tokens, g = _dist.exchange_fused(table, mu, ln=ln)
+                else:
+                    local_tokens = ops.gather_rows(table, mu, ln=ln)
+                    g = _dist.exchange_global_tokens(local_tokens)          # the one collective of this path
                 exchanged = True
+        if local_tokens is None:
+            local_tokens = ops.gather_rows(table, mu, ln=ln)                 # merged local tokens [B, L, C]
         if g is not None:                                                    # patch.py:60
             coin = float(draw_scalar(generator, lambda: torch.rand(
                 1, generator=generator, device=generator.device)))                            # patch.py:62
