@@ -174,9 +174,12 @@ __device__ __forceinline__ float fa_row_max(const uint32_t (&r)[NCH][32], int n_
 }
 // P = exp2(s*c - mc) for 32 scores -> 16 packed fp16 pairs; accumulates the fp32 row sum.  The kernel is bound by
 // MUFU.EX2 (16/clk/SM) for small head_dim, so every POLY_EVERY-th pair is evaluated on the FMA pipe instead
-// (ex2_poly3): the two pipes run side by side.
+// (ex2_poly3): the two pipes run side by side.  A polynomial costs ~9 issue slots against 1 for MUFU, and the
+// kernel is as close to its issue limit (64 %) as to the MUFU limit (54 %), so the share matters: measured at
+// B=2, L=10241, 8 heads x 40 (ms for qkv + flash + out): none 0.603, every 3rd pair 0.674, 4th 0.615, 5th 0.581,
+// 8th 0.589, 16th 0.587; head_dim 64: 0.416 / 0.424 / 0.417 / 0.395 / 0.403 / 0.405.
 #ifndef VTM_FA_POLY_EVERY
-#define VTM_FA_POLY_EVERY 4
+#define VTM_FA_POLY_EVERY 5
 #endif
 template <bool TAIL>
 __device__ __forceinline__ void fa_exp32(const uint32_t (&r)[32], uint32_t (&pk)[16], float c, float mc, int col0,
