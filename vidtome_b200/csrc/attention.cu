@@ -81,9 +81,12 @@ struct HeadSplitEpi {
       gemm::warp_store_rows64(scratch, pk, [&](int, int, const uint4& v) {
         if (bb < nb && n_ok) {
           *reinterpret_cast<uint4*>(dst) = v;
-          if (last_group) {
+          if (last_group && d < DP) {
+            // padding columns: zeros — except column d of V, which holds 1.0 so that the P V MMA also produces
+            // the softmax denominator (flash_attn_kernel, ONES)
             const uint4 z = make_uint4(0, 0, 0, 0);
-            for (int pe = d; pe < DP; pe += 8) *reinterpret_cast<uint4*>(dst + 8 + (pe - d)) = z;
+            *reinterpret_cast<uint4*>(dst + 8) = which == 2 ? make_uint4(0x00003C00u, 0, 0, 0) : z;
+            for (int pe = d + 8; pe < DP; pe += 8) *reinterpret_cast<uint4*>(dst + 8 + (pe - d)) = z;
           }
         }
         ll += 4;                                              // next row of this lane: 4 further down
@@ -181,7 +184,7 @@ __device__ __forceinline__ float fa_row_max(const uint32_t (&r)[NCH][32], int n_
 #ifndef VTM_FA_POLY_EVERY
 #define VTM_FA_POLY_EVERY 5
 #endif
-template <bool TAIL>
+template <bool TAIL, bool SUM>
 __device__ __forceinline__ void fa_exp32(const uint32_t (&r)[32], uint32_t (&pk)[16], float c, float mc, int col0,
                                          int n_valid, float& sum0, float& sum1) {
 #pragma unroll
@@ -200,13 +203,20 @@ __device__ __forceinline__ void fa_exp32(const uint32_t (&r)[32], uint32_t (&pk)
       if (col0 + 2 * i >= n_valid) p0 = 0.f;
       if (col0 + 2 * i + 1 >= n_valid) p1 = 0.f;
     }
-    sum0 += p0;
-    sum1 += p1;
+    if (SUM) {
+      sum0 += p0;
+      sum1 += p1;
+    }
     pk[i] = pack_f16x2(p0, p1);
   }
 }
 
-template <int KSTEPS>
+// ONES: head_dim % 16 == 8 (40, the SD1.5 full-resolution blocks): column d of the padded V rows holds 1.0 and lies
+// inside the P V MMA's N, so O[:, d] accumulates the row sums of P — the denominator comes out of the tensor core,
+// follows every rescale of O automatically and is the sum of exactly the fp16 P values the numerator uses; the
+// softmax warps drop one FADD per score.  Measured effect on time: -0.6 % at L=10241, none at L=21300 (same-box
+// A/B against -DVTM_FA_NO_ONES) — the row sums were not what limits the softmax warps.
+template <int KSTEPS, bool ONES>
 __global__ void __launch_bounds__(FA_THREADS, FaCfg<KSTEPS>::MIN_CTAS)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                   const __grid_constant__ CUtensorMap tm_v, const FaParams p) {
@@ -395,7 +405,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             m3 = fmax3(m3, __uint_as_float(r[ch][i + 6]), __uint_as_float(r[ch][i + 7]));
           }
           uint32_t pk[16];
-          fa_exp32<false>(r[ch], pk, c, mc0, 32 * ch, n_valid, sum0, sum1);
+          fa_exp32<false, !ONES>(r[ch], pk, c, mc0, 32 * ch, n_valid, sum0, sum1);
           tmem_st_32x32b_x16(s_addr + 16 * ch, pk);
         }
         const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
@@ -413,12 +423,12 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) {
           uint32_t pk[16];
-          if (tail) fa_exp32<true>(r[ch], pk, c, mc, 32 * ch, n_valid, sum0, sum1);
-          else fa_exp32<false>(r[ch], pk, c, mc, 32 * ch, n_valid, sum0, sum1);
+          if (tail) fa_exp32<true, !ONES>(r[ch], pk, c, mc, 32 * ch, n_valid, sum0, sum1);
+          else fa_exp32<false, !ONES>(r[ch], pk, c, mc, 32 * ch, n_valid, sum0, sum1);
           tmem_st_32x32b_x16(s_addr + 16 * ch, pk);
         }
       }
-      l_run = l_run * alpha + (sum0 + sum1);
+      if (!ONES) l_run = l_run * alpha + (sum0 + sum1);
       // ---- O rescale: only when a reference max moved, and only after P_{j-1} V_{j-1} has retired
       if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
         mbar_wait(o_ready((j - 1) & 1), ((j - 1) >> 1) & 1u);
@@ -440,6 +450,12 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     }
     mbar_wait(o_ready((nkv - 1) & 1), ((nkv - 1) >> 1) & 1u);
     tc_fence_after();
+    if (ONES) {   // the denominator is column d of O
+      uint32_t r[16];
+      tmem_ld_32x32b_x16(tmem_o + lane_field + (p.d & ~15), r);
+      tmem_ld_wait();
+      l_run = __uint_as_float(r[8]);   // d % 16 == 8
+    }
     if (nparts == 1) {
       // ---- epilogue: O / l -> fp16 -> o[b, row, h*d : h*d + d]
       const float inv = 1.f / l_run;
@@ -537,8 +553,8 @@ constexpr int FA_MAX_SPLIT_UNITS = 320;
 constexpr int FA_MAX_SPLITS = 8;
 constexpr size_t FA_PART_BYTES = static_cast<size_t>(FA_MAX_SPLIT_UNITS) * BQ * (128 * sizeof(float) + sizeof(float2));
 
-template <int KSTEPS>
-int launch_fa(const void* qkvh, __half* o, void* part_ws, int B, int L, int C, int H, int d, float scale,
+template <int KSTEPS, bool ONES>
+int launch_fa_impl(const void* qkvh, __half* o, void* part_ws, int B, int L, int C, int H, int d, float scale,
               cudaStream_t stream) {
   using Cf = FaCfg<KSTEPS>;
   CUtensorMap tq, tk, tv;
@@ -552,13 +568,13 @@ int launch_fa(const void* qkvh, __half* o, void* part_ws, int B, int L, int C, i
   if (rc) return rc;
   rc = make_tmap_3d_f16(&tv, base + 2 * which_stride, DP, L, BH, DP, static_cast<uint64_t>(L) * DP, 64, Cf::BKV);
   if (rc) return rc;
-  rc = cuda_rc(cudaFuncSetAttribute(flash_attn_kernel<KSTEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  rc = cuda_rc(cudaFuncSetAttribute(flash_attn_kernel<KSTEPS, ONES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(Cf::SMEM_BYTES)));
   if (rc) return rc;
   int sms = 0, per_sm = 0;
   rc = gemm::device_sms(&sms);
   if (rc) return rc;
-  rc = cuda_rc(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flash_attn_kernel<KSTEPS>, FA_THREADS,
+  rc = cuda_rc(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flash_attn_kernel<KSTEPS, ONES>, FA_THREADS,
                                                              Cf::SMEM_BYTES));
   if (rc) return rc;
   const int slots = sms * (per_sm > 0 ? per_sm : 1);
@@ -597,12 +613,21 @@ int launch_fa(const void* qkvh, __half* o, void* part_ws, int B, int L, int C, i
   p.part_o = reinterpret_cast<float*>(static_cast<char*>(part_ws) +
                                       static_cast<size_t>(FA_MAX_SPLIT_UNITS) * BQ * sizeof(float2));
   const long long units = p.n_full + (tiles - p.n_full) * splits;
-  flash_attn_kernel<KSTEPS><<<static_cast<unsigned>(units), FA_THREADS, Cf::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  flash_attn_kernel<KSTEPS, ONES><<<static_cast<unsigned>(units), FA_THREADS, Cf::SMEM_BYTES, stream>>>(tq, tk, tv, p);
   rc = launch_rc();
   if (rc || splits == 1) return rc;
   const long long work = static_cast<long long>(rem) * BQ * (d / 8);
   fa_combine_kernel<<<static_cast<unsigned>((work + 255) / 256), 256, 0, stream>>>(p, Cf::DV_N, rem);
   return launch_rc();
+}
+
+template <int KSTEPS>
+int launch_fa(const void* qkvh, __half* o, void* part_ws, int B, int L, int C, int H, int d, float scale,
+              cudaStream_t stream) {
+#if !defined(VTM_FA_NO_ONES)   // A/B switch: keep the denominator in the softmax warps
+  if (d % 16 == 8) return launch_fa_impl<KSTEPS, true>(qkvh, o, part_ws, B, L, C, H, d, scale, stream);
+#endif
+  return launch_fa_impl<KSTEPS, false>(qkvh, o, part_ws, B, L, C, H, d, scale, stream);
 }
 
 }  // namespace
