@@ -213,3 +213,40 @@ def test_markstein_division_used_by_k0_is_exact():
         rem = (x.astype(np.float64) - q0.astype(np.float64) * np.float64(n32)).astype(np.float32)
         q = (q0.astype(np.float64) + rem.astype(np.float64) * np.float64(r)).astype(np.float32)
         assert np.array_equal(q, x / n32)
+
+
+def test_device_resident_randf_descriptor_validation():
+    """vtm_split_t.randf_dev (CUDA-graph capture): counts must not depend on the draw, i.e. F % stride == 0."""
+    from vidtome_b200._lib import VtmSplit
+    lib = _lib()
+    ns, nd = ctypes.c_int32(), ctypes.c_int32()
+    fake = ctypes.c_void_p(0x1000)                      # never dereferenced by the host helper
+    ok = VtmSplit(0, 8 * 64, 0, 8, 64, 4, 3, 0, fake)  # `randf` (3) is ignored when randf_dev is set
+    assert lib.vtm_split_counts(ctypes.byref(ok), ctypes.byref(ns), ctypes.byref(nd)) == 0
+    assert (ns.value, nd.value) == (6 * 64, 2 * 64)
+    bad = VtmSplit(0, 6 * 64, 0, 6, 64, 4, 0, 0, fake)  # 6 frames, stride 4: 1 or 2 dst frames depending on randf
+    assert lib.vtm_split_counts(ctypes.byref(bad), ctypes.byref(ns), ctypes.byref(nd)) == -3
+    with pytest.raises(RuntimeError, match="int32 CUDA tensor"):
+        VtmSplit.local(8 * 64, 0, 8, 4, torch.zeros(1, dtype=torch.int32))      # CPU tensor
+
+
+def test_draw_randf_replays_the_reference_draw_on_cpu():
+    """Eagerly, draw_randf is exactly the reference's `torch.randint(0, stride, [1], generator=...)` (merge.py:56-57)."""
+    from vidtome_b200 import utils
+    g1 = torch.Generator().manual_seed(9)
+    g2 = torch.Generator().manual_seed(9)
+    want = [int(torch.randint(0, s, torch.Size([1]), generator=g1)) for s in (4, 4, 2, 4, 3)]
+    got = [utils.draw_randf(g2, s, 8) for s in (4, 4, 2, 4, 3)]
+    assert got == want and all(isinstance(v, int) for v in got)
+
+
+def test_cuda_graph_mode_rejects_dynamic_work():
+    from vidtome_b200.driver import ChunkedDenoiser
+    net = _skeleton()
+    with pytest.raises(ValueError, match="cuda_graph"):
+        ChunkedDenoiser(net, merge_global=True, cuda_graph=True)
+    with pytest.raises(ValueError, match="cuda_graph"):
+        ChunkedDenoiser(net, randomize_chunks=True, cuda_graph=True)
+    den = ChunkedDenoiser(net, cuda_graph=True)        # CPU tensors simply keep stepping eagerly
+    assert den._graph is None
+
