@@ -264,11 +264,20 @@ int sm_count(int* sms) {
 // that all warps run the same number of iterations (+-1) instead of a short last wave.
 template <class K>
 int grid_for_rows(K kernel, long long rows, int rows_per_warp, int sms) {
-  static int per_sm = 0;        // one instance per kernel instantiation
+  // occupancy per kernel (all instantiations of one template share the function-pointer TYPE, so the cache is keyed
+  // by the pointer value); a handful of entries, filled once each
+  static const void* known[32];
+  static int occ[32];
+  static int n_known = 0;
+  const void* key = reinterpret_cast<const void*>(kernel);
+  int per_sm = 0;
+  for (int i = 0; i < n_known; ++i)
+    if (known[i] == key) per_sm = occ[i];
   if (per_sm == 0) {
     int n = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, ROW_THREADS, 0) != cudaSuccess || n < 1) n = 2;
     per_sm = n;
+    if (n_known < 32) { known[n_known] = key; occ[n_known] = n; ++n_known; }
   }
   const long long warps = (rows + rows_per_warp - 1) / rows_per_warp;
   long long blocks = (warps + (ROW_THREADS / 32) - 1) / (ROW_THREADS / 32);
