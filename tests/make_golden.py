@@ -244,9 +244,21 @@ def main():
                        (4, 4), B, 15, merge_global=True, align_batch=True)
     case_compute_merge("compute_merge_skip_ds4", [chunk(4, 4, 128)], (8, 8), B, 16)          # downsample 4 > 2: no merge
     # ---- block level (reference ToMeBlock, fp16 CPU)
+    # (later additions are generated AFTER the block fixtures below, from their own generator, so that the fixtures
+    #  above stay byte-identical when this script is re-run)
     hid = video_tokens(rng, 2, 4, 64, 128, np.float16).reshape(8, 64, 128)
     case_block("block_ratio1", hid, (8, 8), 2, 21, 128, 2, local_merge_ratio=1.0)
     case_block("block_ratio09", hid, (8, 8), 2, 22, 128, 2, local_merge_ratio=0.9)
+    # ---- additions: the default PnP configuration (3 samples, align_batch, configs/default.yaml:25,56) with global
+    #      merging over two chunks, and a low local ratio over three levels' worth of frames
+    rng2 = np.random.default_rng(321)
+    def chunk3(F, T, C):
+        return exact_video_tokens(rng2, 3, F, T, C).reshape(3 * F, T, C)
+    case_compute_merge("compute_merge_exact_pnp_b3", [chunk3(4, 16, 128), chunk3(4, 16, 128)], (4, 4), 3, 31,
+                       merge_global=True, align_batch=True)
+    case_compute_merge("compute_merge_exact_ratio05_f8",
+                       [exact_video_tokens(rng2, 2, 8, 16, 128).reshape(16, 16, 128)], (4, 4), 2, 32,
+                       local_merge_ratio=0.5)
 
 
 if __name__ == "__main__":

@@ -16,7 +16,7 @@ def load(name):
 
 
 def test_fixtures_present():
-    assert len(glob.glob(os.path.join(GOLD, "*.npz"))) >= 19
+    assert len(glob.glob(os.path.join(GOLD, "*.npz"))) >= 21
 
 
 def _check_match(g, m: O.Match, exact: bool):
@@ -67,7 +67,8 @@ def _args(g):
 
 @pytest.mark.parametrize("name", ["compute_merge_exact_f16", "compute_merge_exact_f8_align",
                                   "compute_merge_exact_f6", "compute_merge_exact_global",
-                                  "compute_merge_exact_global_align", "compute_merge_skip_ds4"])
+                                  "compute_merge_exact_global_align", "compute_merge_skip_ds4",
+                                  "compute_merge_exact_pnp_b3", "compute_merge_exact_ratio05_f8"])
 def test_compute_merge_matches_reference(name):
     g = load(name)
     glob_tokens = None
