@@ -259,6 +259,17 @@ def main():
     case_compute_merge("compute_merge_exact_ratio05_f8",
                        [exact_video_tokens(rng2, 2, 8, 16, 128).reshape(16, 16, 128)], (4, 4), 2, 32,
                        local_merge_ratio=0.5)
+    # ---- oracle-only additions (replayed by tests/test_oracle_golden.py): odd frame count, stride 2, every src token
+    #      merged (ratio 1.0), and both branches of the global coin forced (global_rand 0.0 / 1.0)
+    def chunk2(F, T, C):
+        return exact_video_tokens(rng2, 2, F, T, C).reshape(2 * F, T, C)
+    case_compute_merge("compute_merge_exact_f5", [chunk2(5, 16, 128)], (4, 4), 2, 33)
+    case_compute_merge("compute_merge_exact_stride2_f8", [chunk2(8, 16, 128)], (4, 4), 2, 34, target_stride=2)
+    case_compute_merge("compute_merge_exact_ratio1_f4", [chunk2(4, 16, 128)], (4, 4), 2, 35, local_merge_ratio=1.0)
+    case_compute_merge("compute_merge_exact_global_rand0", [chunk2(4, 16, 128), chunk2(4, 16, 128)], (4, 4), 2, 36,
+                       merge_global=True, global_rand=0.0)
+    case_compute_merge("compute_merge_exact_global_rand1", [chunk2(4, 16, 128), chunk2(4, 16, 128)], (4, 4), 2, 37,
+                       merge_global=True, global_rand=1.0)
 
 
 if __name__ == "__main__":

@@ -16,7 +16,7 @@ def load(name):
 
 
 def test_fixtures_present():
-    assert len(glob.glob(os.path.join(GOLD, "*.npz"))) >= 21
+    assert len(glob.glob(os.path.join(GOLD, "*.npz"))) >= 26
 
 
 def _check_match(g, m: O.Match, exact: bool):
@@ -68,7 +68,10 @@ def _args(g):
 @pytest.mark.parametrize("name", ["compute_merge_exact_f16", "compute_merge_exact_f8_align",
                                   "compute_merge_exact_f6", "compute_merge_exact_global",
                                   "compute_merge_exact_global_align", "compute_merge_skip_ds4",
-                                  "compute_merge_exact_pnp_b3", "compute_merge_exact_ratio05_f8"])
+                                  "compute_merge_exact_pnp_b3", "compute_merge_exact_ratio05_f8",
+                                  "compute_merge_exact_f5", "compute_merge_exact_stride2_f8",
+                                  "compute_merge_exact_ratio1_f4", "compute_merge_exact_global_rand0",
+                                  "compute_merge_exact_global_rand1"])
 def test_compute_merge_matches_reference(name):
     g = load(name)
     glob_tokens = None
