@@ -9,7 +9,6 @@ restatement exists for timing only; on exact-arithmetic inputs its merged tokens
 import json
 import os
 import sys
-import types
 
 import torch
 
