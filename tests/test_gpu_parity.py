@@ -119,7 +119,10 @@ def _tome_info(g):
 @pytest.mark.parametrize("name", ["compute_merge_exact_f16", "compute_merge_exact_f8_align",
                                   "compute_merge_exact_f6", "compute_merge_exact_global",
                                   "compute_merge_exact_global_align", "compute_merge_skip_ds4",
-                                  "compute_merge_exact_pnp_b3", "compute_merge_exact_ratio05_f8"])
+                                  "compute_merge_exact_pnp_b3", "compute_merge_exact_ratio05_f8",
+                                  "compute_merge_exact_f5", "compute_merge_exact_stride2_f8",
+                                  "compute_merge_exact_ratio1_f4", "compute_merge_exact_global_rand0",
+                                  "compute_merge_exact_global_rand1"])
 def test_compute_merge_bit_exact_vs_reference(name, monkeypatch):
     from types import SimpleNamespace
     from vidtome_b200 import patch
