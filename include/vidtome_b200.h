@@ -206,7 +206,7 @@ int vtm_unmerge_add(const void* y_dev, int64_t y_batch_stride, const int32_t* ma
  * math restated in the reference at utils/pnp_utils.py:47-95): q,k,v = x Wq^T, x Wk^T, x Wv^T (no bias),
  * per-head softmax(q k^T * scale) v, heads re-joined, y = o Wo^T + bo.
  *   x_dev [B, L, C] fp16; w_qkv_dev [3C, C] fp16 (rows: Wq | Wk | Wv, torch Linear layout);
- *   w_o_dev [C, C] fp16; b_o_dev [C] fp16 (may be NULL); heads * head_dim == C; head_dim <= 160
+ *   w_o_dev [C, C] fp16; b_o_dev [C] fp16 (may be NULL); heads * head_dim == C; head_dim % 8 == 0 and head_dim <= 128 (else VTM_E_SHAPE / VTM_E_UNSUPPORTED)
  *   y_dev [B, L, C] fp16; ws_dev workspace of vtm_attention_workspace_bytes(B, L, C, heads) bytes (q/k/v head-major
  *   with rows padded to 64 or 128 halfs, plus the attention output before the out projection).
  */

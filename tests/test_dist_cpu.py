@@ -45,6 +45,15 @@ def _worker(rank, world, port, out_dir):
         draws = [torch.zeros_like(draw) for _ in range(world)]
         dist.all_gather(draws, draw)
         assert all(int(d) == int(draw) for d in draws)
+        # lock-step check: equal chunk counts pass and report uniform / ragged lengths; unequal counts
+        # raise on EVERY rank instead of leaving one of them waiting in a collective
+        assert vd.check_step_lockstep([4, 4]) is True
+        assert vd.check_step_lockstep([4, 4] if rank == 0 else [4, 2]) is False
+        try:
+            vd.check_step_lockstep([4, 4, 4] if rank == 0 else [4, 4])
+            raise AssertionError("unequal chunk counts must raise")
+        except RuntimeError as e:
+            assert "different numbers of chunks" in str(e)
         np.save(os.path.join(out_dir, f"glob{rank}.npy"), glob.numpy())
         np.save(os.path.join(out_dir, f"local{rank}.npy"), local.numpy())
     finally:

@@ -250,3 +250,110 @@ def test_cuda_graph_mode_rejects_dynamic_work():
     den = ChunkedDenoiser(net, cuda_graph=True)        # CPU tensors simply keep stepping eagerly
     assert den._graph is None
 
+
+
+# --------------------------------------------------------------------------- round 2: lifecycle on a ControlNet pipeline
+def test_lifecycle_on_controlnet_pipeline_matches_reference_trace():
+    """apply / update / collect / remove on a fake StableDiffusionControlNetPipeline (two skeleton nets) reach the
+    same modules and return the same objects as the reference did (tests/golden/lifecycle_controlnet.json, written by
+    tests/make_golden_r02.py from vidtome/patch.py:292-295,337-387): update_patch / collect_from_patch look for
+    `.controlnet` on the object passed in, remove_patch on the UNet."""
+    import json
+    import sys
+    import vidtome_b200
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    want = json.load(open(os.path.join(ROOT, "tests", "golden", "lifecycle_controlnet.json")))
+
+    def factory():
+        from vidtome_b200.skeleton import make_skeleton
+
+        class DiffusionPipeline:
+            pass
+
+        class StableDiffusionControlNetPipeline(DiffusionPipeline):
+            def __init__(self):
+                self.unet = make_skeleton("tiny", device="cpu", dtype=torch.float32, seed=1)
+                self.controlnet = make_skeleton("tiny", device="cpu", dtype=torch.float32, seed=2)
+        return StableDiffusionControlNetPipeline()
+
+    # the same tracing code that produced the fixture, minus the reference import
+    src = open(os.path.join(ROOT, "tests", "make_golden_r02.py")).read()
+    ns = {}
+    start, end = src.index("def lifecycle_trace"), src.index("def case_mean")
+    exec(src[start:end], ns)
+    got = ns["lifecycle_trace"](vidtome_b200, factory)
+    assert got == want
+
+
+def test_update_patch_resets_controlnet_global_tokens():
+    """with include_control=True and merge_global, update_patch(pipe, global_tokens=None) must reach the
+    ControlNet blocks too, otherwise last step's global tokens leak into the next step."""
+    import vidtome_b200
+    from vidtome_b200.skeleton import make_skeleton
+
+    class StableDiffusionControlNetPipeline:
+        def __init__(self):
+            self.unet = make_skeleton("tiny", device="cpu", dtype=torch.float32)
+            self.controlnet = make_skeleton("tiny", device="cpu", dtype=torch.float32)
+
+    class DiffusionPipeline(StableDiffusionControlNetPipeline):
+        pass
+    pipe = DiffusionPipeline()
+    vidtome_b200.apply_patch(pipe, include_control=True, merge_global=True)
+    for net in (pipe.unet, pipe.controlnet):
+        for b in net.blocks:
+            b.global_tokens = torch.zeros(1)
+    vidtome_b200.update_patch(pipe, global_tokens=None)
+    assert all(b.global_tokens is None for net in (pipe.unet, pipe.controlnet) for b in net.blocks)
+
+
+def test_kd_fast_path_only_for_stock_attention_modules():
+    """KD reads to_q/to_k/to_v/to_out[0].weight directly, so it may replace attn1.forward only when that
+    cannot change the result.  LoRA-style wrappers (still exposing .weight), custom processors, hooks, instance
+    forward overrides (PnP) and the Attention options that alter the math must all fall back to self.attn1(...)."""
+    from vidtome_b200 import patch
+    from vidtome_b200.skeleton import Attention
+
+    def fresh():
+        return Attention(64, 2, 32)
+    assert patch._plain_attention_module(fresh())
+
+    class LoRACompatibleLinear(torch.nn.Linear):          # diffusers' wrapper: a Linear subclass with an extra term
+        def forward(self, x):
+            return super().forward(x) + 1.0
+    a = fresh(); a.to_q = LoRACompatibleLinear(64, 64, bias=False)
+    assert not patch._plain_attention_module(a)
+
+    class PeftLike(torch.nn.Module):                      # PEFT: wraps the base layer, forwards .weight / .bias
+        def __init__(self, base):
+            super().__init__(); self.base_layer = base
+        weight = property(lambda self: self.base_layer.weight)
+        bias = property(lambda self: self.base_layer.bias)
+        def forward(self, x):
+            return self.base_layer(x) * 2
+    a = fresh(); a.to_out[0] = PeftLike(a.to_out[0])
+    assert not patch._plain_attention_module(a)
+
+    class LoRAAttnProcessor:
+        pass
+
+    class AttnProcessor2_0:
+        pass
+    a = fresh(); a.processor = LoRAAttnProcessor()
+    assert not patch._plain_attention_module(a)
+    a = fresh(); a.processor = AttnProcessor2_0()
+    assert patch._plain_attention_module(a)
+    a = fresh(); a.register_forward_hook(lambda m, i, o: o)
+    assert not patch._plain_attention_module(a)
+    a = fresh(); a.to_v.register_forward_pre_hook(lambda m, i: None)
+    assert not patch._plain_attention_module(a)
+    a = fresh(); a.forward = lambda *args, **kw: None     # PnP's injected forward (utils/pnp_utils.py:99-101)
+    assert not patch._plain_attention_module(a)
+    for attr, val in (("residual_connection", True), ("rescale_output_factor", 2.0), ("group_norm", torch.nn.GroupNorm(1, 64)),
+                      ("added_kv_proj_dim", 8)):
+        a = fresh(); setattr(a, attr, val)
+        assert not patch._plain_attention_module(a), attr
+    a = fresh(); a.to_out[1] = torch.nn.Dropout(0.5); a.train()
+    assert not patch._plain_attention_module(a)
+    a = fresh(); a.to_k = torch.nn.Linear(64, 64, bias=True)
+    assert not patch._plain_attention_module(a)

@@ -32,10 +32,38 @@ def rank() -> int:
 
 
 def shard_chunks(chunks: Sequence, rank_: Optional[int] = None, world_: Optional[int] = None) -> List:
-    """Round-robin assignment of a step's chunk list to ranks (chunk i -> rank i % world)."""
+    """Round-robin assignment of a step's chunk list to ranks (chunk i -> rank i % world).
+
+    Contract for the collective exchange modes (`patch.GLOBAL_EXCHANGE` = "allgather" / "p2p"): every merged block
+    forward issues one collective (or one symmetric-memory barrier), so EVERY rank must run the same number of UNet
+    forwards per step — `len(chunks)` must be a multiple of the world size.  `check_step_lockstep` verifies that
+    (and whether the chunks are equally long, which the fused p2p exchange additionally needs) once per step; the
+    driver calls it before the first forward of the step."""
     r = rank() if rank_ is None else rank_
     w = world() if world_ is None else world_
     return [c for i, c in enumerate(chunks) if i % w == r]
+
+
+def check_step_lockstep(local_chunk_lens: Sequence[int], group=None) -> bool:
+    """Collective sanity check, once per denoising step, before any block-level exchange: all-gathers every
+    rank's list of chunk lengths (frames).  Raises on ALL ranks (so nobody is left waiting in a collective) when
+    the ranks would run different numbers of UNet forwards — e.g. the reference's random first-chunk length
+    (generate.py:176-178) changed the chunk count so that it no longer divides by the world size.  Returns True
+    when all chunks of all ranks have the same length (token counts then agree at every block: the fused
+    peer-to-peer exchange is usable), False when they are ragged (only the padded all-gather is)."""
+    w = world()
+    lens = [int(v) for v in local_chunk_lens]
+    if w == 1:
+        return len(set(lens)) <= 1
+    everyone = [None] * w
+    dist.all_gather_object(everyone, lens, group=group)
+    counts = [len(v) for v in everyone]
+    if len(set(counts)) != 1:
+        raise RuntimeError(
+            f"vidtome_b200.dist: ranks would run different numbers of chunks this step ({counts}); the global-token "
+            "exchange issues one collective per merged block and needs lock-step ranks. Use a chunk count that is a "
+            "multiple of the world size (pad with a repeated chunk) or patch.GLOBAL_EXCHANGE = 'recurrence'.")
+    return len({n for v in everyone for n in v}) <= 1
 
 
 def seed_all_ranks(seed: int) -> None:

@@ -37,7 +37,7 @@ class ChunkedDenoiser:
     def __init__(self, unet: torch.nn.Module, n_timesteps: int = 50, chunk_size: int = 16,
                  guidance_scale: float = 7.5, merge_global: bool = False, chunk_ord: str = "seq",
                  perm_div: int = 4, randomize_chunks: bool = False, cond: Optional[torch.Tensor] = None,
-                 cuda_graph: bool = False, graph_warmup: int = 2):
+                 cuda_graph: bool = False, graph_warmup: int = 2, shard: bool = False):
         """`cuda_graph=True`: after `graph_warmup` eager steps, the noise prediction of a whole step (every chunk:
         CFG batch, UNet forward with the merge path, guidance combine) is captured once into a CUDA graph and
         replayed; per step the host then issues one graph launch plus the DDIM update instead of ~250 kernel
@@ -46,6 +46,10 @@ class ChunkedDenoiser:
         and bit-identical latents — as eager stepping.  Needs static shapes and chunk order: local merging only
         (`merge_global=False`), `randomize_chunks=False`, frame counts divisible by the target stride."""
         self.unet = unet
+        # shard=True: this process is one rank of a torch.distributed job and takes chunks i % world == rank of every
+        # step (dist.shard_chunks); with merge_global and a collective exchange mode the ranks are checked for
+        # lock-step once per step (dist.check_step_lockstep)
+        self.shard = bool(shard)
         self.cuda_graph = bool(cuda_graph)
         self.graph_warmup = int(graph_warmup)
         self._graph = None          # (CUDAGraph, static x, static timestep, static noise, shape)
@@ -111,9 +115,22 @@ class ChunkedDenoiser:
         pred_x0 = (x - sigma * eps) / mu
         return mu_prev * pred_x0 + sigma_prev * eps
 
+    def _step_chunks(self, flen: int) -> List[torch.Tensor]:
+        chunks = self.get_chunks(flen)
+        if not self.shard:
+            return chunks
+        from . import dist as _dist
+        chunks = _dist.shard_chunks(chunks)
+        if self.merge_global and patch.GLOBAL_EXCHANGE in ("allgather", "p2p") and _dist.world() > 1:
+            uniform = _dist.check_step_lockstep([len(c) for c in chunks])
+            if not uniform and patch.GLOBAL_EXCHANGE == "p2p":
+                raise RuntimeError("GLOBAL_EXCHANGE='p2p' needs equally long chunks on every rank (fixed chunking); "
+                                   "use 'allgather' for ragged chunks")
+        return chunks
+
     def _all_noises(self, x: torch.Tensor, t) -> torch.Tensor:
         noises = torch.zeros_like(x)
-        for chunk in self.get_chunks(len(x)):
+        for chunk in self._step_chunks(len(x)):
             # chunks are contiguous frame ranges (possibly visited in another order): slice instead of indexing with
             # a host tensor, which would cost a synchronous host->device copy per chunk per step
             lo, hi = int(chunk[0]), int(chunk[-1]) + 1

@@ -183,23 +183,53 @@ def compute_merge(module: torch.nn.Module, x: torch.Tensor, tome_info: Dict[str,
     return m, u, merged
 
 
+# attention processors whose result is plain softmax(q k^T * scale) v (what KD computes)
+_PLAIN_PROCESSORS = ("AttnProcessor", "AttnProcessor2_0", "XFormersAttnProcessor")
+
+
 def _plain_attention_module(attn: torch.nn.Module) -> bool:
-    """True if `attn` is a stock diffusers-style Attention whose forward we may replace with KD:
-    to_q/to_k/to_v without bias, to_out = [Linear, Dropout], and no instance-level forward override
-    (PnP installs one, utils/pnp_utils.py:99-101)."""
+    """True only if replacing `attn.forward` by KD cannot change the result: `attn` is a stock diffusers-style
+    Attention whose projections are bare `torch.nn.Linear` (exact type: LoRA-compatible or PEFT-wrapped layers
+    carry extra terms and still expose `.weight`), to_q/to_k/to_v without bias, to_out = [Linear, Dropout(inactive)],
+    no instance-level forward override (PnP installs one, utils/pnp_utils.py:99-101), no forward hooks, a default
+    attention processor (or none), and none of the Attention options that alter the math (group / spatial norm,
+    residual connection, output rescale, added KV projections).  Anything else goes through `self.attn1(...)`
+    exactly as the reference does (patch.py:157-162), e.g. after `pipe.load_lora_weights` (generate.py:93-94)."""
     if "forward" in vars(attn):
         return False
     need = ("to_q", "to_k", "to_v", "to_out", "heads")
     if not all(hasattr(attn, n) for n in need):
         return False
-    if any(getattr(attn, n).bias is not None for n in ("to_q", "to_k", "to_v")):
-        return False
     to_out = attn.to_out
-    if not (isinstance(to_out, (torch.nn.ModuleList, torch.nn.Sequential)) and isinstance(to_out[0], torch.nn.Linear)):
+    if not isinstance(to_out, (torch.nn.ModuleList, torch.nn.Sequential)) or len(to_out) < 1:
+        return False
+    linears = (attn.to_q, attn.to_k, attn.to_v, to_out[0])
+    if any(type(m) is not torch.nn.Linear for m in linears):
+        return False
+    if any(m.bias is not None for m in linears[:3]):
+        return False
+    for m in (attn,) + linears + tuple(to_out[1:]):
+        if m._forward_hooks or m._forward_pre_hooks or getattr(m, "_forward_hooks_with_kwargs", None):
+            return False
+    for extra in to_out[1:]:
+        if not isinstance(extra, torch.nn.Dropout) or (extra.p > 0 and extra.training):
+            return False
+    proc = getattr(attn, "processor", None)
+    if proc is not None and type(proc).__name__ not in _PLAIN_PROCESSORS:
+        return False
+    if getattr(attn, "group_norm", None) is not None or getattr(attn, "spatial_norm", None) is not None:
+        return False
+    if getattr(attn, "norm_cross", None) or getattr(attn, "residual_connection", False):
+        return False
+    if getattr(attn, "rescale_output_factor", 1.0) != 1.0:
+        return False
+    if getattr(attn, "added_kv_proj_dim", None) is not None or getattr(attn, "add_k_proj", None) is not None:
         return False
     C = attn.to_q.weight.shape[1]
     if attn.to_q.weight.shape[0] != C or attn.to_k.weight.shape != attn.to_q.weight.shape:
         return False                       # inner dim != query dim or cross-attention shaped K/V
+    if attn.to_v.weight.shape != attn.to_q.weight.shape or to_out[0].weight.shape != (C, C):
+        return False
     head_dim = C // int(attn.heads)
     return head_dim * int(attn.heads) == C and head_dim % 8 == 0 and head_dim <= 128   # KD's supported range
 
@@ -216,7 +246,7 @@ def make_diffusers_tome_block(block_class: Type[torch.nn.Module]) -> Type[torch.
     """Patched class for a diffusers BasicTransformerBlock (patch.py:119-203)."""
 
     class ToMeBlock(block_class):
-        # Save for unpatching later
+        # the original class, restored by remove_patch
         _parent = block_class
 
         def forward(self, hidden_states, attention_mask=None, encoder_hidden_states=None,
@@ -294,15 +324,16 @@ def hook_tome_model(model: torch.nn.Module):
 
 
 def hook_tome_module(module: torch.nn.Module):
-    """Forward pre-hook that forks the default RNG into `module.generator` on first use, so that all
+    """Forward pre-hook that gives the block its own `module.generator`, forked from the default RNG of the
+    input's device the first time the block runs (and again if the block moves to another device), so that all
     blocks draw the same random target frames within one pass (patch.py:215-231)."""
     def hook(module, args):
-        if not hasattr(module, "generator"):
-            module.generator = init_generator(args[0].device)
-        elif module.generator.device != args[0].device:
-            module.generator = init_generator(args[0].device, fallback=module.generator)
-        else:
-            return None
+        device = args[0].device
+        current = getattr(module, "generator", None)
+        if current is None:
+            module.generator = init_generator(device)
+        elif current.device != device:
+            module.generator = init_generator(device, fallback=current)
         return None
 
     module._tome_info["hooks"].append(module.register_forward_pre_hook(hook))
@@ -332,18 +363,17 @@ def apply_patch(
      - seed: stored, unused (as in the reference).   - batch_size: number of video chunks per pass (2 = CFG, 3 = PnP).
      - align_batch: share one matching across the batch (PnP).   - target_stride: one target frame per this many frames.
     """
-    # Make sure the module is not currently patched
+    # start from an unpatched model: a second apply_patch must not stack hooks or subclasses
     remove_patch(model)
 
     is_diffusers = isinstance_str(model, "DiffusionPipeline") or isinstance_str(model, "ModelMixin")
 
     if not is_diffusers:
         if not hasattr(model, "model") or not hasattr(model.model, "diffusion_model"):
-            # Provided model not supported
             raise RuntimeError("Provided model was not a Stable Diffusion / Latent Diffusion model, as expected.")
         diffusion_model = model.model.diffusion_model
     else:
-        # Supports "pipe.unet" and "unet"
+        # a pipeline carries its UNet as `.unet`; a bare UNet is used as is
         diffusion_model = model.unet if hasattr(model, "unet") else model
 
     if isinstance_str(model, "StableDiffusionControlNetPipeline") and include_control:
@@ -380,7 +410,7 @@ def apply_patch(
                 module._tome_info = diffusion_model._tome_info
                 hook_tome_module(module)
 
-                # Something needed for older versions of diffusers
+                # blocks of diffusers releases that predate the ada-norm flags: read as "plain LayerNorm"
                 if not hasattr(module, "use_ada_layer_norm_zero") and is_diffusers:
                     module.use_ada_layer_norm = False
                     module.use_ada_layer_norm_zero = False
@@ -388,22 +418,27 @@ def apply_patch(
     return model
 
 
-def _patched_roots(model: torch.nn.Module) -> List[torch.nn.Module]:
-    """The modules the un/update/collect calls walk: `model.unet` (or `model`) and, when that UNet object
-    itself carries one, its `.controlnet`.  (The reference looks for `.controlnet` on the UNet rather than
-    on the pipeline, patch.py:341-344,361-364,376-378, so a ControlNet patched through
-    include_control is not reached by these three calls; kept for drop-in behaviour.)"""
+def _roots_of(model: torch.nn.Module, controlnet_owner: torch.nn.Module) -> List[torch.nn.Module]:
+    """[UNet (or the model itself)] + [controlnet_owner.controlnet] when that attribute exists.
+
+    The three lifecycle calls of the reference differ in WHERE they look for `.controlnet`:
+      * remove_patch rebinds `model` to the UNet first (patch.py:341-344), so it looks on the UNet — a ControlNet
+        patched through `include_control=True` is therefore not reached by remove_patch;
+      * update_patch / collect_from_patch keep the object they were given (patch.py:361-364, :376-378), so on a
+        pipeline they DO reach `pipe.controlnet`.
+    Both behaviours are reproduced; the caller passes the object the reference would test."""
     root = model.unet if hasattr(model, "unet") else model
     roots = [root]
-    if hasattr(root, "controlnet"):
-        roots.append(root.controlnet)
+    if hasattr(controlnet_owner, "controlnet"):
+        roots.append(controlnet_owner.controlnet)
     return roots
 
 
 def remove_patch(model: torch.nn.Module):
     """Undo apply_patch if the model is patched: drop the hooks and restore the block classes
-    (patch.py:337-355).  Returns the UNet (or the model itself), like the reference."""
-    roots = _patched_roots(model)
+    (patch.py:337-355).  Returns what the reference returns: the last module it walked."""
+    unet = model.unet if hasattr(model, "unet") else model
+    roots = _roots_of(model, unet)                       # `.controlnet` is looked up on the UNet here
     for root in roots:
         for _, module in root.named_modules():
             info = getattr(module, "_tome_info", None)
@@ -417,21 +452,24 @@ def remove_patch(model: torch.nn.Module):
 
 
 def update_patch(model: torch.nn.Module, **kwargs):
-    """Set attributes on every module that carries `_tome_info` (the UNet and each patched block), e.g.
-    `update_patch(pipe, global_tokens=None)` after each denoising step (patch.py:358-370,
-    generate.py:233-236)."""
-    for root in _patched_roots(model):
+    """Set attributes on every module that carries `_tome_info` (the UNet, each patched block and — on a
+    pipeline that has one — the ControlNet and its blocks), e.g. `update_patch(pipe, global_tokens=None)`
+    after each denoising step (patch.py:358-370, generate.py:233-236).  Like the reference, the return
+    value is the last root walked (its loop variable shadows `model`), not the object passed in."""
+    roots = _roots_of(model, model)                      # `.controlnet` is looked up on the object passed in
+    for root in roots:
         for _, module in root.named_modules():
             if hasattr(module, "_tome_info"):
                 for key, value in kwargs.items():
                     setattr(module, key, value)
-    return model
+    return roots[-1]
 
 
 def collect_from_patch(model: torch.nn.Module, attr="tome"):
-    """{qualified module name: getattr(module, attr)} for every module that has `attr` (patch.py:373-387)."""
+    """{qualified module name: getattr(module, attr)} for every module that has `attr` (patch.py:373-387);
+    a pipeline's ControlNet is included, later roots overwrite equal names exactly as the reference's dict does."""
     found = dict()
-    for root in _patched_roots(model):
+    for root in _roots_of(model, model):
         for name, module in root.named_modules():
             if hasattr(module, attr):
                 found[name] = getattr(module, attr)
