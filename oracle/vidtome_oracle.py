@@ -100,16 +100,29 @@ class Match:
         B, _, c = src.shape
         unm = np.take_along_axis(src, self.unm_idx[:, :, None], axis=1)       # :124
         if mode != "replace":
-            if mode != "mean":
+            # merge.py:126-131: dst.scatter_reduce(-2, dst_idx, src[src_idx], reduce=mode, include_self=True).
+            # Sums are formed exactly (fp64 here; fp16 inputs span < 2^41, far inside the 53-bit mantissa for any
+            # realistic row count) and rounded ONCE; the reference accumulates in the tensor's dtype in index order,
+            # which gives the same result whenever the partial sums are exactly representable (the "exact" fixtures).
+            if mode not in ("mean", "sum", "amax", "amin"):
                 raise NotImplementedError(mode)
-            ct = _compute_dtype(x)
-            s = np.take_along_axis(src, self.src_idx[:, :, None], axis=1).astype(ct)  # :127
-            acc = dst.astype(ct).copy()                                       # include_self=True, :129-131
-            cnt = np.ones((B, dst.shape[1], 1), dtype=ct)
-            for b in range(B):
-                np.add.at(acc[b], self.dst_idx[b], s[b])
-                np.add.at(cnt[b], self.dst_idx[b], 1)
-            dst = (acc / cnt).astype(x.dtype)
+            s = np.take_along_axis(src, self.src_idx[:, :, None], axis=1)        # :127
+            if mode in ("mean", "sum"):
+                acc = dst.astype(np.float64).copy()                           # include_self=True
+                cnt = np.ones((B, dst.shape[1], 1), dtype=np.float64)
+                for b in range(B):
+                    np.add.at(acc[b], self.dst_idx[b], s[b].astype(np.float64))
+                    np.add.at(cnt[b], self.dst_idx[b], 1)
+                if mode == "mean":
+                    # torch: fp16 sum, then div by the count in fp32 -> fp16; with an exact sum that is RN(sum / count)
+                    acc = acc.astype(_compute_dtype(x)) / cnt.astype(_compute_dtype(x))
+                dst = acc.astype(x.dtype)
+            else:
+                acc = dst.copy()
+                fn = np.maximum if mode == "amax" else np.minimum
+                for b in range(B):
+                    fn.at(acc[b], self.dst_idx[b], s[b])
+                dst = acc
         return np.concatenate([unm, dst], axis=1)                             # :133
 
     # merge.py:135-155 (+ :459 for the global matcher)

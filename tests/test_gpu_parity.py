@@ -83,28 +83,19 @@ def test_2s_bit_exact_vs_reference(name):
     assert ret["unm_num"] == int(g["unm_num"])
 
 
-def test_randframe_video_family_tie_tolerant(monkeypatch):
-    """fp16 video-like tokens: the row maxima tie heavily and differ in the last bit between
-    accumulation orders, so indices are compared tie-tolerantly against the oracle's score matrix."""
+def test_randframe_video_family_structure(monkeypatch):
+    """fp16 video-like tokens (heavy last-bit ties): the structural invariants that hold regardless of ties.  The
+    decisions themselves are checked row by row, tie-aware, in tests/test_gpu_parity_scale.py."""
     from vidtome_b200 import merge
     g = load("randframe_video_f16")
     Replay(monkeypatch, randint=g["randf"])
     x = torch.from_numpy(g["x"]).cuda()
     m, u, ret = merge.bipartite_soft_matching_randframe(x, int(g["F"]), float(g["ratio"]), 0, cuda_gen(), 4, False)
     om = O.bipartite_soft_matching_randframe(g["x"], int(g["F"]), float(g["ratio"]), 0, int(g["randf"][0]), 4, False)
-    unm, src, dst, nmax, nidx = m.match.index_tensors(want_node=True)
-    xn = O.normalize_rows(g["x"])
-    s = O.scores_matmul(xn[:, om.a_idx], xn[:, om.b_idx])
-    ours = np.take_along_axis(s, nidx.cpu().numpy()[..., None], -1)[..., 0].astype(np.float32)
-    best = s.max(-1).astype(np.float32)
-    assert (best - ours).max() <= 2 ** -10            # our pick is within one fp16 ulp (at 1.0) of the best
-    assert (nidx.cpu().numpy() == om.node_idx).mean() > 0.9
-    # structural invariants hold regardless of ties
     merged = m(x)
     back = u(merged).cpu().numpy()
     assert merged.shape[1] == ret["unm_num"] + om.num_dst
-    keep = np.concatenate([om.b_idx])
-    np.testing.assert_array_equal(back[:, keep], g["x"][:, keep])     # dst tokens come back unchanged
+    np.testing.assert_array_equal(back[:, om.b_idx], g["x"][:, om.b_idx])     # dst tokens come back unchanged
 
 
 # --------------------------------------------------------------------------- L1 compute_merge
@@ -234,32 +225,86 @@ def _one_block(g):
     return net.cuda().eval()
 
 
-@pytest.mark.parametrize("name,strict", [("block_ratio1", True), ("block_ratio09", False)])
-def test_patched_block_matches_reference_block(name, strict, monkeypatch):
+def _block_fp32_with_our_maps(net, h, ctx, plan):
+    """The block recomputed in fp32 torch ops with the decisions of OUR plan (mu, pi): isolates kernel numerics from
+    last-bit ties in the decisions, which the tie-aware checks cover separately."""
+    blk = net.block.float()
+    B = plan.merged_tokens.shape[0]
+    hf = h.float()
+    nh = blk.norm1(hf)
+    table = nh.reshape(B, -1, nh.shape[-1])
+    mu = plan.mu.long().expand(B, -1)
+    merged = torch.gather(table, 1, mu[..., None].expand(-1, -1, table.shape[-1]))
+    a = blk.attn1(merged)
+    pi = plan.pi.long().expand(B, -1)
+    un = torch.gather(a, 1, pi[..., None].expand(-1, -1, a.shape[-1])).reshape(hf.shape)
+    x = un + hf
+    if blk.attn2 is not None:
+        x = blk.attn2(blk.norm2(x), encoder_hidden_states=ctx.float()) + x
+    if blk.ff is not None:
+        x = blk.ff(blk.norm3(x)) + x
+    net.block.half()
+    return x
+
+
+@pytest.mark.parametrize("name", ["block_ratio1", "block_ratio09"])
+def test_patched_block_matches_reference_block(name, monkeypatch):
+    """Video-like fp16 hidden states (heavy last-bit ties).  Three separate statements instead of
+    "most tokens agree": (1) the match decisions are identical to the oracle's or provable last-bit ties, row by row;
+    (2) with OUR decisions, the block output equals an fp32 recomputation at max-norm 2e-3 (fp16 kernels, fp16 torch
+    cross-attention / feed-forward); (3) against the reference's output: max-norm when no decision flipped, otherwise
+    the tokens that the flips do not touch directly still agree at the median (the flipped keys perturb everyone)."""
     import vidtome_b200
+    from vidtome_b200 import patch
+    from test_gpu_parity_scale import assert_match_tie_aware
     g = load(name)
     net = _one_block(g)
     vidtome_b200.apply_patch(net, batch_size=int(g["batch_size"]), local_merge_ratio=float(g["arg_local_merge_ratio"]))
     assert type(net.block).__name__ == "ToMeBlock"
+    plans = []
+    real = patch.build_merge_plan
+
+    def spy(module, x, info, ln=None):
+        p = real(module, x, info, ln=ln)
+        plans.append(p)
+        return p
+    monkeypatch.setattr(patch, "build_merge_plan", spy)
     Replay(monkeypatch, randint=g["randint"])
     h = torch.from_numpy(g["hidden"]).cuda()
     ctx = torch.from_numpy(g["ctx"]).cuda()
     latent = torch.zeros(h.shape[0], 4, int(g["size"][0]), int(g["size"][1]), device="cuda")
     with torch.no_grad():
         out = net(latent, h, ctx)
+        plan = plans[0]
+        out32 = _block_fp32_with_our_maps(net, h, ctx, plan)
+    # (1) decisions, tie-aware, every row
+    sd = {k[3:]: g[k] for k in g.files if k.startswith("sd_")}
+    nh = O.layer_norm(g["hidden"], sd["block.norm1.weight"], sd["block.norm1.bias"])
+    B = int(g["batch_size"])
+    F = nh.shape[0] // B
+    tok = nh.reshape(B, F * nh.shape[1], -1)
+    rf = int(g["randint"][0])
+    om = O.bipartite_soft_matching_randframe(tok, F, float(g["arg_local_merge_ratio"]), 0, rf, 4, False)
+    xn = O.normalize_rows(tok)
+    s = O.scores_matmul(xn[:, om.a_idx], xn[:, om.b_idx])
+    nflip, _ = assert_match_tie_aware(plan.levels[0], s, om, False)
+    # (2) numerics with our decisions, max-norm
+    scale = out32.abs().max().item()
+    err32 = (out.float() - out32).abs().max().item()
+    print(f"{name}: max-norm error vs fp32 recomputation with our maps: {err32 / scale:.2e}")
+    assert err32 <= 2e-3 * scale
+    # (3) against the reference's own output
     ref = torch.from_numpy(g["out"]).float()
-    err = (out.float().cpu() - ref).abs()
-    scale = ref.abs().max()
-    rel = err.max(-1).values / scale                  # per token
-    if strict:
-        # ratio 1.0: no top-r cut, the result depends only on the arg-max -> 1e-3-relative fp16 agreement
-        assert rel.median() < 1e-3
-        assert (rel < 1e-2).float().mean() > 0.995
+    rel = (out.float().cpu() - ref).abs().max(-1).values / ref.abs().max()
+    res = O.compute_merge(nh, tuple(int(v) for v in g["size"]), batch_size=B,
+                          local_merge_ratio=float(g["arg_local_merge_ratio"]), draw_randf=lambda s_: rf)
+    _, pi_o = O.composed_maps(res, B, tok.shape[1])
+    same_maps = np.array_equal(plan.pi.cpu().numpy().astype(np.int64), pi_o)
+    print(f"{name}: arg-max ties flipped {nflip}, identical unmerge map: {same_maps}, max rel vs reference {rel.max():.2e}")
+    if same_maps:
+        assert rel.max() <= 2e-3
     else:
-        # ratio 0.9: tokens whose row maximum sits at the r-th largest value may fall on the other side
-        # of the cut when the last bit of an fp16 score differs
         assert rel.median() < 1e-3
-        assert (rel < 1e-2).float().mean() > 0.90
     vidtome_b200.remove_patch(net)
     assert type(net.block).__name__ == "BasicTransformerBlock"
 

@@ -36,6 +36,7 @@ class MergePlan:
     levels: List[merge.LevelMatch] = field(default_factory=list)
     randf: List[Any] = field(default_factory=list)      # ints (eager) or 1-element int32 CUDA tensors (graph capture)
     coin: Optional[float] = None
+    mu: Optional[torch.Tensor] = None     # [B'|1, L_local] int32: local merged token i = table row mu[i] (before a global stage)
 
     def unmerge(self, y: torch.Tensor, **kwarg) -> torch.Tensor:
         """u_a of the reference (patch.py:85,168): all unmerges + split_frame, one gather pass."""
@@ -163,7 +164,7 @@ def build_merge_plan(module: torch.nn.Module, x: torch.Tensor, tome_info: Dict[s
     else:
         merged_tokens = ops.gather_rows(table, mu, ln=ln)                    # patch.py:50,56 composed
     return MergePlan(fsize=fsize, N0=N0, merged_tokens=merged_tokens, pi=pi, levels=levels, randf=randfs,
-                     coin=coin)
+                     coin=coin, mu=mu)
 
 
 def compute_merge(module: torch.nn.Module, x: torch.Tensor, tome_info: Dict[str, Any]) -> Tuple[Callable, ...]:
