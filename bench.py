@@ -3,24 +3,32 @@
 
 Workload (config.workload = "sd15_512_f16_chunk_ratio0.9"): one denoising step of an SD1.5-shaped
 skeleton UNet (vidtome_b200/skeleton.py: the 16 transformer blocks of SD1.5 with their (T, C, heads), 10 of
-them merged at max_downsample=2, self-attention section only) on a 16-frame chunk of 512x512 video
-(latents [16, 4, 64, 64], CFG batch 2, fp16), local merge ratio 0.9, followed by the CFG combine and the
-DDIM update (vidtome_b200/driver.py restating generate.py:205-311).  Weights are random (no network for
-checkpoints), data synthetic.
+them merged at max_downsample=2) on a 16-frame chunk of 512x512 video (latents [16, 4, 64, 64], CFG batch 2,
+fp16), local merge ratio 0.9, followed by the CFG combine and the DDIM update (vidtome_b200/driver.py restating
+generate.py:205-311).  `--workload hot` (default) runs the self-attention section of every block (SURVEY §8 rows
+a1-a15); `--workload full` adds each block's cross-attention and GEGLU feed-forward (row f3).  Weights are random
+(no network for checkpoints), data synthetic.
 
-  value   steps/s with the latents already resident in HBM (whole job: N ranks x their chunk)
-  e2e     same step through the public API with HOST latents: pinned host -> device copy of x_t, step,
-          device -> host read of x_{t-1}, all inside the timed region
-  roofline  KA (tcgen05 similarity + arg-max), the dominant kernel: algorithmic FLOPs of every KA launch in
-          the timed region / their CUDA-event durations, against the measured cuBLAS peak
-  cpu_baseline  the numpy oracle of the same path on the host cores, on a bounded sample (N=1, rank 0)
+One JSON line (rank 0):
+  value         steps/s, latents resident in HBM, CUDA-graph replay of the step (whole job: N ranks x their chunk)
+  e2e           same step through the public API with HOST latents: pinned host -> device copy of x_t, step,
+                device -> host read of x_{t-1}, all inside the timed region
+  roofline      KA (tcgen05 similarity + arg-max), the dominant kernel: algorithmic FLOPs of its launches / their
+                CUDA-event durations (a short eager pass: events cannot bracket kernels inside a graph), against the
+                measured cuBLAS peak;  rooflines: the same for KD (attention), K0, KC, KE (HBM-bound row kernels)
+  comparators   measured in the same process on the same GPU (N=1, rank 0):
+                  gpu_reference      the reference's own GPU formulation of the step (baseline/torch_reference_path.py:
+                                     materialised score matrix + max + argsort + gathers/scatters, torch SDPA)
+                  attention_ms       KD vs the module's own attention forward (cuBLAS projections + torch SDPA)
+                  merge_ms_per_call  compute_merge + merge + unmerge + residual, attention excluded (BASELINE metric 2)
+  cpu_baseline  the same restatement in torch fp32 on the host cores, bounded sample (numpy oracle as a second field)
 
-`--impl reference` times the oracle (the CPU restatement of the reference path — the Python reference itself
-cannot travel to the GPU box) on the host cores instead.
+`--impl reference` times that CPU restatement alone (the Python reference itself cannot travel to the GPU box).
 
 Multi-GPU (`--gpus N` under torchrun): local merging makes frame chunks independent (generate.py:216-219), so
 each rank denoises its own 16-frame chunk with replicated weights; nothing crosses GPUs in the data path
 ("scaling": "weak").  Timing = max over ranks of the CUDA-event time between two barriers.
+`--c4-global` (N > 1, opt-in) appends BASELINE config 4 with the global-token exchange (p2p and all-gather).
 """
 from __future__ import annotations
 
@@ -35,9 +43,22 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = "sd15_512_f16_chunk_ratio0.9"
 FRAMES, LATENT = 16, 64
 RATIO = 0.9
+METRIC = "denoising steps/sec (SD1.5, 16-frame chunk)"
+
+
+def workload_name(kind: str) -> str:
+    return "sd15_512_f16_chunk_ratio0.9" + ("" if kind == "hot" else "_full_blocks")
+
+
+def config_dict(world: int, kind: str) -> dict:
+    blocks = ("sd15 census, 10 merged of 16, self-attention section" if kind == "hot" else
+              "sd15 census, 10 merged of 16, self-attention + cross-attention + GEGLU feed-forward")
+    return {"workload": workload_name(kind), "frames_per_chunk": FRAMES, "chunks": world, "latent": [4, LATENT, LATENT],
+            "cfg_batch": 2, "local_merge_ratio": RATIO, "max_downsample": 2, "blocks": blocks,
+            "parallelism": f"chunk-per-gpu x{world}",
+            "l2": "per-step activation traffic (>1 GB) exceeds the 126 MB L2; no explicit flush between steps"}
 
 
 def peaks():
@@ -91,10 +112,41 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------------------------
-def cpu_oracle_blocks(threads: int):
-    """Self-attention section (patch.py:139-169) of one ds1 and one ds2 block of the workload on the host,
-    through the numpy oracle.  Returns callables (ds1, ds2) -> seconds."""
+# ------------------------------------------------------------------------------------------------ CPU legs
+def cpu_torch_block_calls(threads: int):
+    """Self-attention section (patch.py:139-169) of one ds1 and one ds2 block of the workload on the host cores, in
+    fp32 torch ops (the reference's formulation, baseline/torch_reference_path.py).  Returns callables -> seconds."""
+    import torch
+    from baseline import torch_reference_path as R
+    from vidtome_b200.skeleton import BasicTransformerBlock, ModelMixin
+    torch.set_num_threads(threads)
+
+    def make(T, C, heads, ds):
+        class One(ModelMixin):
+            def __init__(self):
+                super().__init__()
+                self.block = BasicTransformerBlock(C, heads)
+
+            def forward(self, latent, hidden):
+                return self.block(hidden)
+        torch.manual_seed(123)
+        net = One().float().eval()
+        R.apply_reference_path(net, RATIO, 2)
+        base = torch.randn(2, 1, T, C)
+        hid = (base + 0.1 * torch.randn(2, FRAMES, T, C)).reshape(2 * FRAMES, T, C)
+        lat = torch.zeros(2 * FRAMES, 4, LATENT, LATENT)
+
+        def run():
+            t0 = time.perf_counter()
+            with torch.no_grad():
+                net(lat, hid)
+            return time.perf_counter() - t0
+        return run
+    return make(4096, 320, 8, 1), make(1024, 640, 8, 2)
+
+
+def cpu_numpy_block_calls():
+    """The numpy oracle of the same two block calls (kept as a second CPU figure)."""
     import numpy as np
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import vidtome_oracle as O
@@ -117,29 +169,143 @@ def cpu_oracle_blocks(threads: int):
 
 
 def run_reference(args):
-    """Reference arm: the oracle port on the host cores.  Step estimate = 5 ds1 + 5 ds2 merged block calls
-    (the 6 un-merged ds4/ds8 blocks are omitted: <1% of the work).  The ds1 call (tens of seconds) is timed
-    once, during warm-up; the ds2 call is timed every step."""
+    """Reference arm: the torch fp32 restatement of the reference path on the host cores, all threads.  A step of
+    the workload is 5 ds1 + 5 ds2 merged block calls (the 6 un-merged ds4/ds8 blocks are <1 % of the work); each
+    timed "step" here is a bounded sample — one ds2 block call, plus one ds1 block call in the first three steps —
+    and the step time is assembled as 5*mean(ds1) + 5*mean(ds2)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    ds1, ds2 = cpu_oracle_blocks(cores)
-    t_ds1 = ds1()
-    for _ in range(max(0, args.warmup - 1)):
+    ds1, ds2 = cpu_torch_block_calls(cores)
+    for _ in range(max(1, min(args.warmup, 2))):
         ds2()
-    t2 = [ds2() for _ in range(max(1, args.steps))]
-    step_s = 5.0 * t_ds1 + 5.0 * (sum(t2) / len(t2))
+    t1, t2 = [], []
+    for i in range(max(1, args.steps)):
+        if i < 3:
+            t1.append(ds1())
+        t2.append(ds2())
+    m1, m2 = sum(t1) / len(t1), sum(t2) / len(t2)
+    step_s = 5.0 * m1 + 5.0 * m2
     val = 1.0 / step_s
-    sample = "numpy oracle: ds1 block call timed once (%.2f s), ds2 block call timed per step (%.3f s); step = 5*ds1 + 5*ds2" % (t_ds1, sum(t2) / len(t2))
+    sample = ("torch fp32 restatement on %d threads: ds1 block call timed %d times (mean %.2f s), ds2 block call timed %d times "
+              "(mean %.3f s); step = 5*ds1 + 5*ds2" % (cores, len(t1), m1, len(t2), m2))
     print(json.dumps({
-        "impl": "reference", "metric": "denoising steps/sec (SD1.5, 16-frame chunk)", "value": val, "unit": "steps/s",
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames": FRAMES, "latent": LATENT, "ratio": RATIO},
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (host)", "data": "synthetic",
+        "config": config_dict(max(1, args.gpus), args.workload),
         "cpu_baseline": {"value": val, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU helpers
+_flush_buf = None
+
+
+def _flush_l2(torch):
+    global _flush_buf
+    if _flush_buf is None:
+        _flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    _flush_buf.fill_(1)
+
+
+def _median_ms(torch, fn, iters=7, warm=2):
+    """Median CUDA-event time of fn(), L2 flushed (256 MiB write) before every timed call."""
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(iters):
+        _flush_l2(torch)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def ka_traffic():
+    """dram bytes of the largest KA launch from the committed ncu --set full capture (profiles/r02_ka_traffic.json,
+    written by tools/ncu_extract.py from the .ncu-rep); None when no capture of this build is committed."""
+    p = os.path.join(ROOT, "profiles", "r02_ka_traffic.json")
+    if not os.path.exists(p):
+        return None
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
+
+
+def comparators(torch, net, dev, steps, kind):
+    """Same-GPU, same-process comparators (N=1).  `net` arrives unpatched."""
+    import vidtome_b200
+    from types import SimpleNamespace
+    from baseline import torch_reference_path as R
+    from vidtome_b200 import ops, patch
+    from vidtome_b200.driver import ChunkedDenoiser
+    out = {"restatement_bit_exact_on_exact_inputs": R.check_exact(dev)}
+
+    # ---- (i) the reference's GPU formulation of the whole step
+    R.apply_reference_path(net, RATIO, 2)
+    den = ChunkedDenoiser(net, n_timesteps=50, chunk_size=FRAMES)
+    g = torch.Generator(device=dev).manual_seed(123)
+    x = torch.randn((FRAMES, 4, LATENT, LATENT), generator=g, device=dev, dtype=torch.float16)
+    for i in range(2):
+        x = den.step(x, i)
+    n = max(3, min(steps, 5))
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for i in range(n):
+        x = den.step(x, i % 50)
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / n
+    R.remove_reference_path(net)
+    out["gpu_reference"] = {"value": round(1e3 / ms, 3), "unit": "steps/s", "ms_per_step": round(ms, 3), "steps": n,
+                            "what": "reference formulation in torch ops on the same GPU (materialised a@b^T, max, argsort, "
+                                    "gather/scatter, torch SDPA attention), same skeleton and weights, eager"}
+
+    # ---- (ii) attention and (iii) merge ms/call at the two merged block shapes of the workload
+    att, mrg = {}, {}
+    for label, T, C, heads in (("C2_ds1", 4096, 320, 8), ("C2_ds2", 1024, 640, 8)):
+        B = 2
+        gg = torch.Generator(device=dev).manual_seed(7)
+        base = torch.randn((B, 1, T, C), generator=gg, device=dev)
+        xf = (base + 0.1 * torch.randn((B, FRAMES, T, C), generator=gg, device=dev)).reshape(B * FRAMES, T, C).half()
+        module = SimpleNamespace(generator=torch.Generator(device=dev).manual_seed(7), global_tokens=None)
+        info = {"size": (LATENT, LATENT), "args": dict(max_downsample=2, batch_size=B, align_batch=False, merge_global=False,
+                                                        global_merge_ratio=0.8, local_merge_ratio=RATIO, global_rand=0.5,
+                                                        target_stride=4)}
+        plan = patch.build_merge_plan(module, xf, info)
+        randfs = [int(r) for r in plan.randf]
+        xj = xf.reshape(B, FRAMES * T, C)
+
+        def ours_merge():
+            p = patch.build_merge_plan(module, xf, info)
+            return p.unmerge_add(p.merged_tokens, xf)
+        ms_o = _median_ms(torch, ours_merge)
+        ms_t = _median_ms(torch, lambda: R.torch_merge_call(xj, FRAMES, T, RATIO, randfs, xj), iters=5)
+        mrg[label] = {"ours_ms": round(ms_o, 4), "torch_reference_path_ms": round(ms_t, 4), "speedup": round(ms_t / ms_o, 2),
+                      "merged_len": int(plan.merged_tokens.shape[1])}
+        L = int(plan.merged_tokens.shape[1])
+        blk = [b for b in net.blocks if b.attn1.to_q.weight.shape[0] == C][0]
+        merged = plan.merged_tokens
+        from vidtome_b200 import attention as A
+        ms_o = _median_ms(torch, lambda: A.self_attention(blk.attn1, merged))
+        with torch.no_grad():
+            ms_t = _median_ms(torch, lambda: blk.attn1(merged))
+        att[label] = {"ours_ms": round(ms_o, 4), "torch_module_ms": round(ms_t, 4), "speedup": round(ms_t / ms_o, 2),
+                      "B": B, "L": L, "C": C, "heads": heads}
+    out["attention_ms"] = dict(att, what="KD (QKV projection + flash attention + out projection) vs the attention module's own "
+                                        "forward (cuBLAS linears + torch scaled_dot_product_attention) on the merged tokens; L2 flushed")
+    out["merge_ms_per_call"] = dict(mrg, what="compute_merge + merge + unmerge + residual for one block, attention excluded; L2 flushed")
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -163,9 +329,15 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     torch.manual_seed(123)
-    net = make_skeleton("sd15", hot_path_only=True, device=dev)
+    kind = args.workload
+    net = make_skeleton("sd15", hot_path_only=(kind == "hot"), device=dev)
     vidtome_b200.apply_patch(net, local_merge_ratio=RATIO, batch_size=2, merge_global=False)
-    den = ChunkedDenoiser(net, n_timesteps=50, chunk_size=FRAMES)
+    cond = None
+    if kind != "hot":
+        gc = torch.Generator(device=dev).manual_seed(5)
+        cond = torch.randn((2, 77, 768), generator=gc, device=dev, dtype=torch.float16)
+    den_eager = ChunkedDenoiser(net, n_timesteps=50, chunk_size=FRAMES, cond=cond)
+    den_graph = ChunkedDenoiser(net, n_timesteps=50, chunk_size=FRAMES, cond=cond, cuda_graph=True)
     g = torch.Generator(device=dev).manual_seed(123 + rank)
     x0 = torch.randn((FRAMES, 4, LATENT, LATENT), generator=g, device=dev, dtype=torch.float16)
     x_host = x0.cpu().pin_memory()
@@ -191,71 +363,110 @@ def run_ours(args):
 
     state = {"x": x0.clone()}
 
-    def dev_step(i):
-        state["x"] = den.step(state["x"], i % 50)
+    def dev_step(i):                                           # latents resident in HBM, graph replay
+        state["x"] = den_graph.step(state["x"], i % 50)
 
-    # The end-to-end leg uses the public API's CUDA-graph mode (one graph replay + the DDIM update per step): with
-    # a host round trip every step the ~250 launches of an eager step are exposed instead of hidden behind the
-    # previous step's kernels.  Same kernels, same results (tests/test_gpu_graph.py).
-    den_e2e = den if args.e2e_eager else ChunkedDenoiser(net, n_timesteps=50, chunk_size=FRAMES, cuda_graph=True)
+    def eager_step(i):
+        state["x"] = den_eager.step(state["x"], i % 50)
 
     def e2e_step(i):
         x = x_host.to(dev, non_blocking=True)                  # H2D of this step's input (pinned)
-        y = den_e2e.step(x, i % 50)
+        y = (den_eager if args.e2e_eager else den_graph).step(x, i % 50)
         out_host.copy_(y, non_blocking=True)                   # D2H of the step's result
         torch.cuda.current_stream().synchronize()              # the caller reads the result
 
     warm = max(3, args.warmup)
-    for i in range(warm):
+    for i in range(warm + 2):                                  # 2 eager steps, capture, then >= 3 replays
         dev_step(i)
     sampler = ClockSampler(local) if rank == 0 else None
-    ops.STATS.reset(time_ka=True)
     ms = timed(dev_step, args.steps)
-    launches = ops.STATS.launches
-    ka = list(ops.STATS.ka_events)
-    ops.STATS.reset(time_ka=False)
     clocks = sampler.stop() if sampler else None
-    for i in range(5):                                         # 2 eager steps, capture, replays
+    for i in range(3):
         e2e_step(i)
     ms_e2e = timed(e2e_step, args.steps)
 
+    # per-kernel pass: eager stepping with every hot kernel bracketed by CUDA events on the launching stream
+    n_k = max(2, min(args.steps, 5))
+    eager_step(0)
+    ops.STATS.reset(timed=("KA", "KD", "K0", "KC", "KE", "KB1"))
+    ms_eager = timed(eager_step, n_k)
+    launches_per_step = ops.STATS.launches / n_k
+    events = dict(ops.STATS.events)
+    ops.STATS.reset()
+
     if rank == 0:
         pk = peaks()
-        ka_ms = sum(s.elapsed_time(e) for s, e, _, _ in ka)
-        ka_flops = sum(f for _, _, f, _ in ka)
-        ka_bytes = sum(b for _, _, _, b in ka)
+
+        def summarise(name):
+            ev = events.get(name, [])
+            t = sum(s.elapsed_time(e) for s, e, _, _ in ev)
+            return t, sum(f for _, _, f, _ in ev), sum(b for _, _, _, b in ev), len(ev)
+        ka_ms, ka_flops, ka_bytes, ka_n = summarise("KA")
         tf = ka_flops / ka_ms / 1e9 if ka_ms > 0 else 0.0
+        tr = ka_traffic()
         roof = {"bound": "tensor", "kernel": "gemm_kernel<256, ArgmaxEpi> (KA sim+argmax)", "achieved": round(tf, 1),
                 "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": round(tf / pk["tf_sust"], 3),
-                "peak_source": pk["src"] + " (sustained cuBLAS bf16: kernel timed inside a long step)",
-                "launches": len(ka), "share_of_step": round(ka_ms / ms, 3),
-                "algorithmic_GB_per_step": round(ka_bytes / args.steps / 1e9, 3),
-                # dram__bytes_read.sum + dram__bytes_write.sum of the largest KA launch of the step (C2 ds1 level 1:
-                # 84.7 MB algorithmic) from the ncu --set full capture in profiles/r01_ka_ncu_summary.md
-                "traffic": 108.5e6, "traffic_launch": "B=2 Ns=49152 Nd=16384 C=320", "traffic_algorithmic": 84.7e6}
+                "frac_of_burst_peak": round(tf / pk["tf_burst"], 3),
+                "peak_source": pk["src"] + " (sustained cuBLAS bf16: kernel timed inside a long step; burst figure beside it)",
+                "launches": ka_n, "share_of_step": round(ka_ms / ms_eager, 3), "timed_in": f"{n_k} eager steps",
+                "algorithmic_GB_per_step": round(ka_bytes / n_k / 1e9, 3),
+                "traffic": None if tr is None else tr.get("dram_bytes"),
+                "traffic_detail": tr}
+        others = {}
+        for name, bound, label in (("KD", "tensor", "vtm_attention: QKV gemm + flash_attn_kernel + out gemm"),
+                                   ("K0", "hbm", "normalize_split_kernel (+ fused LayerNorm)"),
+                                   ("KC", "hbm", "gather_rows_kernel (merge gather, + fused LayerNorm)"),
+                                   ("KE", "hbm", "gather_rows_kernel<ADD> (unmerge + residual)"),
+                                   ("KB1", "hbm", "radix_sort_fused_kernel (latency-bound: 3 grid barriers)")):
+            t, fl, by, n = summarise(name)
+            if n == 0 or t <= 0:
+                continue
+            if bound == "tensor":
+                a = fl / t / 1e9
+                others[name] = {"bound": "tensor", "kernel": label, "achieved": round(a, 1), "peak": pk["tf_burst"],
+                                "unit": "TFLOP/s", "frac": round(a / pk["tf_burst"], 3), "launches": n,
+                                "ms_per_step": round(t / n_k, 4), "share_of_step": round(t / ms_eager, 3),
+                                "note": "head_dim 40/80: the softmax exponentials (MUFU) bound this kernel before the tensor pipe does"}
+            else:
+                a = by / t / 1e6
+                others[name] = {"bound": "hbm", "kernel": label, "achieved": round(a, 1), "peak": pk["hbm"], "unit": "GB/s",
+                                "frac": round(a / pk["hbm"], 3), "launches": n, "ms_per_step": round(t / n_k, 4),
+                                "share_of_step": round(t / ms_eager, 3)}
         value = world * args.steps / (ms / 1e3)
         out = {
-            "metric": "denoising steps/sec (SD1.5, 16-frame chunk)", "value": round(value, 3), "unit": "steps/s",
+            "metric": METRIC, "value": round(value, 3), "unit": "steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": round(ms / args.steps, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_chunk": FRAMES, "chunks": world, "latent": [4, LATENT, LATENT],
-                       "cfg_batch": 2, "local_merge_ratio": RATIO, "max_downsample": 2, "blocks": "sd15 census, 10 merged of 16, self-attention section",
-                       "parallelism": f"chunk-per-gpu x{world}", "l2": "per-step activation traffic (>1 GB) exceeds the 126 MB L2; no explicit flush"},
+            "config": config_dict(world, kind),
+            "value_mode": "cuda_graph replay (ChunkedDenoiser(cuda_graph=True)), latents resident",
             "clocks": clocks,
             "e2e": {"value": round(world * args.steps / (ms_e2e / 1e3), 3), "unit": "steps/s",
                     "h2d_bytes_per_step": x_host.numel() * 2, "d2h_bytes_per_step": out_host.numel() * 2,
                     "ms_per_step": round(ms_e2e / args.steps, 3),
                     "mode": "eager" if args.e2e_eager else "cuda_graph replay (ChunkedDenoiser(cuda_graph=True))"},
-            "gpu_launches": launches,
+            "gpu_launches": int(round(launches_per_step * args.steps)),
+            "gpu_launches_note": "kernels of this library per step (counted over the eager pass) x steps; the timed region replays them from a CUDA graph",
+            "eager_ms_per_step": round(ms_eager / n_k, 3),
             "roofline": roof,
+            "rooflines": others,
         }
+        if world == 1 and not args.no_gpu_ref:
+            vidtome_b200.remove_patch(net)
+            out["comparators"] = comparators(torch, net, dev, args.steps, kind)
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
-            ds1, ds2 = cpu_oracle_blocks(cores)
+            ds1, ds2 = cpu_torch_block_calls(cores)
             t1, t2 = ds1(), min(ds2(), ds2())
             step_s = 5 * t1 + 5 * t2
-            out["cpu_baseline"] = {"value": round(1.0 / step_s, 5), "unit": "steps/s", "cores": cores, "kind": "port",
-                                   "sample": "numpy oracle, self-attention section of 1 ds1 block (%.2f s) and 1 ds2 block (%.3f s); step = 5*ds1 + 5*ds2" % (t1, t2)}
+            cb = {"value": round(1.0 / step_s, 5), "unit": "steps/s", "cores": cores, "kind": "port",
+                  "sample": "torch fp32 restatement of the reference path (baseline/torch_reference_path.py), self-attention section "
+                            "of 1 ds1 block (%.2f s) and 1 ds2 block (%.3f s); step = 5*ds1 + 5*ds2" % (t1, t2)}
+            if not args.no_numpy:
+                n1, n2 = cpu_numpy_block_calls()
+                u1, u2 = n1(), n2()
+                cb["numpy_oracle"] = {"value": round(1.0 / (5 * u1 + 5 * u2), 5), "unit": "steps/s",
+                                      "sample": "numpy oracle, same two block calls (%.2f s, %.3f s)" % (u1, u2)}
+            out["cpu_baseline"] = cb
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -267,7 +478,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="hot", choices=["hot", "full"],
+                    help="hot = self-attention section of every block (SURVEY §8 a1-a15); full = + cross-attention and feed-forward (f3)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-numpy", action="store_true", help="skip the numpy-oracle second CPU figure")
+    ap.add_argument("--no-gpu-ref", action="store_true", help="skip the same-GPU comparators")
     ap.add_argument("--e2e-eager", action="store_true", help="end-to-end leg without CUDA-graph replay")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -15,18 +15,39 @@ from ._lib import VtmSplit, check
 
 
 class _Stats:
-    """Launch accounting for bench.py: `launches` counts the CUDA kernels this library enqueued;
-    when `time_ka` is set, every KA launch is bracketed by CUDA events on the launching stream."""
+    """Launch accounting for bench.py: `launches` counts the CUDA kernels this library enqueued; with
+    `reset(timed={"KA", "KD", ...})` every call of the named ops is bracketed by CUDA events on the launching stream
+    and recorded in `events[name]` as (start, end, algorithmic FLOPs, algorithmic bytes)."""
     launches = 0
-    time_ka = False
-    ka_events = []      # (start_event, end_event, flops, bytes)
+    timed = frozenset()
+    events = {}
 
     @classmethod
-    def reset(cls, time_ka: bool = False):
-        cls.launches, cls.time_ka, cls.ka_events = 0, time_ka, []
+    def reset(cls, timed=()):
+        cls.launches, cls.timed, cls.events = 0, frozenset(timed), {}
 
 
 STATS = _Stats
+
+
+class _Timed:
+    """Context manager: CUDA-event bracket around one op when STATS asks for it (no-op otherwise)."""
+    __slots__ = ("name", "flops", "bytes", "ev")
+
+    def __init__(self, name: str, flops: float, nbytes: float):
+        self.name, self.flops, self.bytes, self.ev = name, flops, nbytes, None
+
+    def __enter__(self):
+        if self.name in STATS.timed:
+            self.ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self.ev[0].record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ev is not None:
+            self.ev[1].record()
+            STATS.events.setdefault(self.name, []).append((self.ev[0], self.ev[1], self.flops, self.bytes))
+        return False
 
 
 def _stream() -> int:
@@ -82,9 +103,10 @@ def normalize_split(x: torch.Tensor, rowmap: Optional[torch.Tensor], split: VtmS
         _require(rowmap, torch.int32, "rowmap")
         map_bs = 0 if rowmap.shape[0] == 1 else rowmap.shape[1]
     lw, lb, eps = _ln_args(ln)
-    check(_lib.load().vtm_normalize_split_ln(x.data_ptr(), x.stride(0), _ptr(rowmap), map_bs, C.byref(split),
-                                             B, Cc, lw, lb, eps, a.data_ptr(), b.data_ptr(), _stream()),
-          "vtm_normalize_split_ln")
+    with _Timed("K0", 0.0, 4.0 * B * (ns + nd) * Cc):            # read N rows, write N rows
+        check(_lib.load().vtm_normalize_split_ln(x.data_ptr(), x.stride(0), _ptr(rowmap), map_bs, C.byref(split),
+                                                 B, Cc, lw, lb, eps, a.data_ptr(), b.data_ptr(), _stream()),
+              "vtm_normalize_split_ln")
     STATS.launches += 1
     return a, b
 
@@ -97,16 +119,9 @@ def sim_argmax(a: torch.Tensor, b: torch.Tensor, align_batch: bool, simt: bool =
     Nd = b.shape[1]
     keys = torch.empty((1 if align_batch else B, Ns), dtype=torch.int64, device=a.device)
     fn = _lib.load().vtm_sim_argmax_simt if simt else _lib.load().vtm_sim_argmax
-    ev = None
-    if STATS.time_ka:
-        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-        ev[0].record()
-    check(fn(a.data_ptr(), b.data_ptr(), B, Ns, Nd, Cc, int(bool(align_batch)), keys.data_ptr(), _stream()),
-          "vtm_sim_argmax")
-    if ev is not None:
-        ev[1].record()
-        STATS.ka_events.append((ev[0], ev[1], 2.0 * B * Ns * Nd * Cc,
-                                2.0 * B * (Ns + Nd) * Cc + 8.0 * keys.shape[0] * Ns))
+    with _Timed("KA", 2.0 * B * Ns * Nd * Cc, 2.0 * B * (Ns + Nd) * Cc + 8.0 * keys.shape[0] * Ns):
+        check(fn(a.data_ptr(), b.data_ptr(), B, Ns, Nd, Cc, int(bool(align_batch)), keys.data_ptr(), _stream()),
+              "vtm_sim_argmax")
     STATS.launches += 1
     return keys
 
@@ -120,8 +135,9 @@ def topr_sort(keys: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=keys.device)
     edge = torch.empty((Bp, Ns), dtype=torch.int32, device=keys.device)
     rank = torch.empty((Bp, Ns), dtype=torch.int32, device=keys.device)
-    check(lib.vtm_topr_sort(keys.data_ptr(), Bp, Ns, edge.data_ptr(), rank.data_ptr(), ws.data_ptr(),
-                            ws_bytes, _stream()), "vtm_topr_sort")
+    with _Timed("KB1", 0.0, 24.0 * Bp * Ns):
+        check(lib.vtm_topr_sort(keys.data_ptr(), Bp, Ns, edge.data_ptr(), rank.data_ptr(), ws.data_ptr(),
+                                ws_bytes, _stream()), "vtm_topr_sort")
     # one cooperative launch when all (tiles x Bp) CTAs are co-resident (2 per SM), else 6 small launches
     STATS.launches += 1 if ((Ns + 1023) // 1024) * Bp <= 2 * torch.cuda.get_device_properties(keys.device).multi_processor_count else 6
     return edge, rank
@@ -179,8 +195,9 @@ def gather_rows(x: torch.Tensor, row_map: Optional[torch.Tensor], L: Optional[in
     if out is None:
         out = torch.empty((B, L, Cc), dtype=torch.float16, device=x.device)
     lw, lb, eps = _ln_args(ln)
-    check(_lib.load().vtm_gather_rows_ln(x.data_ptr(), x.stride(0), _ptr(row_map), map_bs, B, L, Cc, lw, lb, eps,
-                                         out.data_ptr(), out.stride(0), _stream()), "vtm_gather_rows_ln")
+    with _Timed("KC", 0.0, 4.0 * B * L * Cc + 4.0 * B * L):       # read L rows, write L rows, + map
+        check(_lib.load().vtm_gather_rows_ln(x.data_ptr(), x.stride(0), _ptr(row_map), map_bs, B, L, Cc, lw, lb, eps,
+                                             out.data_ptr(), out.stride(0), _stream()), "vtm_gather_rows_ln")
     STATS.launches += 1
     return out
 
@@ -218,8 +235,11 @@ def unmerge_add(y: torch.Tensor, row_map: torch.Tensor, resid: Optional[torch.Te
     if resid is not None:
         _require(resid, torch.float16, "resid")
     out = torch.empty((B, N, Cc), dtype=torch.float16, device=y.device)
-    check(_lib.load().vtm_unmerge_add(y.data_ptr(), y.stride(0), row_map.data_ptr(), map_bs, _ptr(resid),
-                                      B, N, Cc, out.data_ptr(), _stream()), "vtm_unmerge_add")
+    L = y.shape[1]
+    nbytes = 2.0 * B * (L + (2 if resid is not None else 1) * N) * Cc + 4.0 * B * N    # B(L + 2N)C*2 + map
+    with _Timed("KE", 0.0, nbytes):
+        check(_lib.load().vtm_unmerge_add(y.data_ptr(), y.stride(0), row_map.data_ptr(), map_bs, _ptr(resid),
+                                          B, N, Cc, out.data_ptr(), _stream()), "vtm_unmerge_add")
     STATS.launches += 1
     return out
 
@@ -250,8 +270,9 @@ def attention(x: torch.Tensor, w_qkv: torch.Tensor, w_o: torch.Tensor, b_o: Opti
     ws_bytes = lib.vtm_attention_workspace_bytes(B, L, Cc, heads)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
     y = torch.empty_like(x)
-    check(lib.vtm_attention(x.data_ptr(), w_qkv.data_ptr(), w_o.data_ptr(), _ptr(b_o), B, L, Cc, heads,
-                            float(scale), y.data_ptr(), ws.data_ptr(), ws_bytes, _stream()), "vtm_attention")
+    with _Timed("KD", 4.0 * B * L * L * Cc + 8.0 * B * L * Cc * Cc, 4.0 * B * L * Cc + 8.0 * Cc * Cc):
+        check(lib.vtm_attention(x.data_ptr(), w_qkv.data_ptr(), w_o.data_ptr(), _ptr(b_o), B, L, Cc, heads,
+                                float(scale), y.data_ptr(), ws.data_ptr(), ws_bytes, _stream()), "vtm_attention")
     STATS.launches += 3
     return y
 
