@@ -63,8 +63,18 @@ __global__ void k(float* out, long long* cyc, int iters) {
         REP8(X)
 #undef X
       }
-      if (MODE == 9) {  // cvt.rn.f16x2.f32 (F2FP)
-#define X(i) asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h[i]) : "f"(f[i]), "f"(f[i + 8]));
+      if (MODE == 10) {  // LOP3 reference for MODE 9's extra xor
+#define X(i) asm volatile("xor.b32 %0, %0, %1;" : "+r"(h[i]) : "r"(h[7 - i]));
+        REP8(X)
+#undef X
+      }
+      if (MODE == 11 || MODE == 12) {  // 8 MUFU + 8 F2FP(+8 xor): does F2FP share the XU pipe?
+#define X(i) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(f[i]));
+        REP8(X)
+#undef X
+      }
+      if (MODE == 9 || MODE == 12) {  // cvt.rn.f16x2.f32 (F2FP) + xor
+#define X(i) { unsigned q_; asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(q_) : "f"(f[i]), "f"(f[i + 8])); h[i] ^= q_; }
         REP8(X)
 #undef X
       }
@@ -104,7 +114,10 @@ int main() {
     run<6>("8 FFMA2 + 8 MUFU", w, 16);
     run<7>("16 FFMA2 + 8 MUFU", w, 24);
     run<8>("FMNMX3", w, 8);
-    run<9>("F2FP cvt.f16x2", w, 8);
+    run<9>("8 F2FP + 8 LOP3", w, 16);
+    run<10>("LOP3", w, 8);
+    run<11>("8 MUFU", w, 8);
+    run<12>("8 MUFU + 8 F2FP + 8 LOP3", w, 24);
   }
   return 0;
 }

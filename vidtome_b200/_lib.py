@@ -11,7 +11,8 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvidtome_b200.so")
+# VIDTOME_B200_LIB: tuning tools load an alternative build of the SAME library (tools/sweep_fa_poly.py); never a fallback
+LIB_PATH = os.environ.get("VIDTOME_B200_LIB") or os.path.join(_HERE, "libvidtome_b200.so")
 
 
 class VtmSplit(C.Structure):

@@ -175,27 +175,33 @@ __device__ __forceinline__ float fa_row_max(const uint32_t (&r)[NCH][32], int n_
   }
   return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 }
-// P = exp2(s*c - mc) for 32 scores -> 16 packed fp16 pairs; accumulates the fp32 row sum.  The kernel is bound by
-// MUFU.EX2 (16/clk/SM) for small head_dim, so every POLY_EVERY-th pair is evaluated on the FMA pipe instead
-// (ex2_poly3): the two pipes run side by side.  A polynomial costs ~9 issue slots against 1 for MUFU, and the
-// kernel is as close to its issue limit (64 %) as to the MUFU limit (54 %), so the share matters: measured at
-// B=2, L=10241, 8 heads x 40 (ms for qkv + flash + out): none 0.603, every 3rd pair 0.674, 4th 0.615, 5th 0.581,
-// 8th 0.589, 16th 0.587; head_dim 64: 0.416 / 0.424 / 0.417 / 0.395 / 0.403 / 0.405.
-#ifndef VTM_FA_POLY_EVERY
-#define VTM_FA_POLY_EVERY 5
+// P = exp2(s*c - mc) for 32 scores -> 16 packed fp16 pairs; accumulates the fp32 row sum.  For small head_dim the
+// kernel is bound by MUFU.EX2 (16/clk/SM) and by issue slots about equally, so (i) x = s*c - mc is one packed FFMA2 per
+// PAIR of scores, and (ii) VTM_FA_POLY_NUM of every VTM_FA_POLY_DEN pairs are evaluated on the FMA/ALU pipes with the
+// packed cubic (ex2_poly3_x2: 10 issue slots per pair against 2 MUFU) while the others go to MUFU: the two pipes run
+// side by side (tools/ubench/fma2_pipe.cu: 16 FFMA2 + 8 MUFU take 74 cycles, 8 MUFU alone 65).  Per score and SMSP:
+// MUFU 8 (1 - phi) cycles, issue 2.5 + 4 phi slots — balanced near phi = 0.45.  Swept on B200 (tools/sweep_fa_poly.py,
+// ms for qkv + flash + out at B=2, L=10241, 8 heads x 40): see profiles/r02_attention_poly_sweep.md.
+#ifndef VTM_FA_POLY_NUM
+#define VTM_FA_POLY_NUM 7
+#endif
+#ifndef VTM_FA_POLY_DEN
+#define VTM_FA_POLY_DEN 16
 #endif
 template <bool TAIL, bool SUM>
 __device__ __forceinline__ void fa_exp32(const uint32_t (&r)[32], uint32_t (&pk)[16], float c, float mc, int col0,
                                          int n_valid, float& sum0, float& sum1) {
+  const uint64_t c2 = f32x2_pack(c, c), nmc2 = f32x2_pack(-mc, -mc);
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    const float x0 = fmaf(__uint_as_float(r[2 * i]), c, -mc);
-    const float x1 = fmaf(__uint_as_float(r[2 * i + 1]), c, -mc);
+    const uint64_t x2 = f32x2_fma(f32x2_pack(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), c2, nmc2);
     float p0, p1;
-    if (VTM_FA_POLY_EVERY > 0 && (i % VTM_FA_POLY_EVERY) == VTM_FA_POLY_EVERY - 1) {
-      p0 = ex2_poly3(x0);
-      p1 = ex2_poly3(x1);
+    // pair i goes to the polynomial when the running count floor((i+1) NUM / DEN) steps: an even spread
+    if (((i + 1) * VTM_FA_POLY_NUM) / VTM_FA_POLY_DEN != (i * VTM_FA_POLY_NUM) / VTM_FA_POLY_DEN) {
+      ex2_poly3_x2(x2, p0, p1);
     } else {
+      float x0, x1;
+      f32x2_unpack(x2, x0, x1);
       p0 = ex2_approx(x0);
       p1 = ex2_approx(x1);
     }

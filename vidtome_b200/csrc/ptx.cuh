@@ -345,6 +345,53 @@ __device__ __forceinline__ float ex2_poly3(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
+// ---------------------------------------------------------------- packed fp32 (two lanes per instruction, sm_100)
+// FFMA2 / FADD2 run at the same per-element rate as FFMA (tools/ubench/fma2_pipe.cu: 2.1 cycles per warp instruction
+// against 1.03) but take HALF the issue slots — and the softmax warps of the flash kernel are issue-bound as much as
+// MUFU-bound.  Operands are 64-bit register pairs {lo, hi}.
+__device__ __forceinline__ uint64_t f32x2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f32x2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f32x2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f32x2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t f32x2_sub(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// exp2 of a PAIR on the FMA/ALU pipes: the Cody-Waite split and the cubic of ex2_poly3 on packed lanes (6 packed
+// instructions for two values), clamp and exponent insertion per lane (2 + 2).  Same numerics as ex2_poly3.
+__device__ __forceinline__ void ex2_poly3_x2(uint64_t x2, float& p0, float& p1) {
+  float x0, x1;
+  f32x2_unpack(x2, x0, x1);
+  x2 = f32x2_pack(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
+  const uint64_t magic = f32x2_pack(12582912.f, 12582912.f);
+  const uint64_t t2 = f32x2_add(x2, magic);
+  const uint64_t f2 = f32x2_sub(x2, f32x2_sub(t2, magic));
+  uint64_t q2 = f32x2_fma(f32x2_pack(0.05517160892486572f, 0.05517160892486572f), f2,
+                          f32x2_pack(0.2426111102104187f, 0.2426111102104187f));
+  q2 = f32x2_fma(q2, f2, f32x2_pack(0.6932609677314758f, 0.6932609677314758f));
+  q2 = f32x2_fma(q2, f2, f32x2_pack(0.9999280571937561f, 0.9999280571937561f));
+  float q0, q1, t0, t1;
+  f32x2_unpack(q2, q0, q1);
+  f32x2_unpack(t2, t0, t1);
+  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+}
+
 // ---------------------------------------------------------------- misc
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
