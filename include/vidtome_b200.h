@@ -192,6 +192,23 @@ int vtm_gather_rows_ln(const void* x_dev, int64_t x_batch_stride, const int32_t*
                        const void* ln_bias_dev, float ln_eps, void* y_dev, int64_t y_batch_stride, void* stream);
 
 /*
+ * Merge with a reduction — the non-"replace" modes of the merge closure, vidtome/merge.py:126-131:
+ * `dst.scatter_reduce(-2, dst_idx, src[src_idx], reduce=mode, include_self=True)` followed by `cat([unm, dst])`.
+ *   mode: 1 = "mean", 2 = "sum", 3 = "amax", 4 = "amin" ("prod" is not implemented: VTM_E_UNSUPPORTED)
+ *   x_dev [B, split->N, C] fp16 (the tensor being merged; finite values), keys/edge [Bp, Ns] from KA / KB1, r as in KB2
+ *   y_dev [B, (Ns - r) + Nd, C] fp16;  ws_dev: vtm_merge_reduce_workspace_bytes(B, Nd, C) bytes
+ * Sums are exact and order independent (int64 fixed-point accumulators, value * 2^24) and rounded once; the mean is
+ * fp16(float(sum) / float(count)) as torch computes it.  The reference accumulates in fp16 (CPU: index order; CUDA:
+ * atomics in arbitrary order) and therefore agrees bit for bit only where its partial sums are exact.
+ * No caller in the reference passes a mode; a reduction is not a row gather, so this is an operator-API entry and
+ * not part of the composed per-block plan.
+ */
+size_t vtm_merge_reduce_workspace_bytes(int32_t B, int32_t Nd, int32_t C);
+int vtm_merge_reduce(const void* x_dev, int64_t x_batch_stride, const vtm_split_t* split, int32_t r, int32_t Bp,
+                     const uint64_t* keys_dev, const int32_t* edge_dev, int32_t B, int32_t C, int32_t mode,
+                     void* y_dev, void* ws_dev, size_t ws_bytes, void* stream);
+
+/*
  * KE — unmerge gather fused with the residual add: out[b, p, :] = y[b, map[b, p], :] + resid[b, p, :].
  * Replaces unmerge() of every level (zeros + 3 scatter_, vidtome/merge.py:135-155, :439-460),
  * split_frame (vidtome/utils.py:37-40) and `attn_output + hidden_states` (vidtome/patch.py:168-169).

@@ -446,3 +446,37 @@ def test_config3_global_recurrence_through_driver():
     L = 333
     assert lengths == [L, L, 2 * L - int(L * 0.8), 2 * L - int(L * 0.8)] or sorted(lengths) == sorted([L, L, 2 * L - int(L * 0.8), 2 * L - int(L * 0.8)])
     assert all(getattr(b, "global_tokens", None) is None for b in net.blocks)   # reset by post_iter
+
+
+# --------------------------------------------------------------------------- merge modes (f4: scatter_reduce)
+@pytest.mark.parametrize("name", ["randframe_mean_exact_f4", "randframe_mean_exact_f4_align", "2s_mean_exact",
+                                  "randframe_mean_fp16_video"])
+def test_merge_modes_vs_reference_and_oracle(name, monkeypatch):
+    """merge(x, mode) for mean / sum / amax / amin (merge.py:126-131): bit-exact against the REFERENCE's output on the
+    exact family (its fp16 partial sums are exact there) and for amax / amin always; on real-valued fp16 data bit-exact
+    against the ORACLE (same exact-sum-rounded-once definition) and within fp16 accumulation error of the reference."""
+    from vidtome_b200 import merge
+    g = load(name)
+    x = torch.from_numpy(g["x"]).cuda()
+    if str(g["kind"]) == "randframe":
+        Replay(monkeypatch, randint=g["randf"])
+        m, u, ret = merge.bipartite_soft_matching_randframe(x, int(g["F"]), float(g["ratio"]), int(g["unm_pre"]), cuda_gen(),
+                                                            4, bool(g["align"]))
+        om = O.bipartite_soft_matching_randframe(g["x"], int(g["F"]), float(g["ratio"]), int(g["unm_pre"]),
+                                                 int(g["randf"][0]), 4, bool(g["align"]))
+    else:
+        m, u, ret = merge.bipartite_soft_matching_2s(x, int(g["src_len"]), float(g["ratio"]), bool(g["align"]), unmerge_chunk=0)
+        om = O.bipartite_soft_matching_2s(g["x"], int(g["src_len"]), float(g["ratio"]), bool(g["align"]), unmerge_chunk=0)
+    exact = "exact" in name
+    if exact:
+        np.testing.assert_array_equal(m(x).cpu().numpy(), g["merged_replace"])
+    # on the video family the match itself may differ from the oracle's by last-bit ties: feed the oracle OUR indices
+    unm, src, dst = m.match.index_tensors()
+    om.unm_idx, om.src_idx, om.dst_idx = unm[..., 0].cpu().numpy(), src[..., 0].cpu().numpy(), dst[..., 0].cpu().numpy()
+    for mode in ("mean", "sum", "amax", "amin"):
+        got = m(x, mode=mode).cpu().numpy()
+        np.testing.assert_array_equal(got, om.merge(g["x"], mode=mode), err_msg=f"{mode} vs oracle")
+        if exact:
+            np.testing.assert_array_equal(got, g["merged_" + mode], err_msg=f"{mode} vs reference")
+    with pytest.raises(NotImplementedError):
+        m(x, mode="prod")

@@ -83,6 +83,11 @@ def test_compute_entry_points_validate_arguments_without_a_device():
     assert lib.vtm_gather_rows(None, 0, None, 0, 1, 1, 8, None, 0, None) == -1
     assert lib.vtm_topr_sort(1, 1, 16, 1, 1, 1, 0, None) == -4                # workspace too small
     assert lib.vtm_linear_f16(1, 1, None, 16, 12, 64, 1, 12, None) == -2
+    from vidtome_b200._lib import VtmSplit
+    sp = VtmSplit.prefix(20, 8)
+    assert lib.vtm_merge_reduce(1, 0, ctypes.byref(sp), 4, 1, 1, 1, 2, 16, 9, 1, 1, 1 << 30, None) == -6   # unknown mode
+    assert lib.vtm_merge_reduce(1, 0, ctypes.byref(sp), 4, 1, 1, 1, 2, 16, 1, 1, 1, 16, None) == -4        # workspace
+    assert lib.vtm_merge_reduce_workspace_bytes(2, 12, 16) >= 2 * 12 * 16 * 8 + 2 * 12 * 4
     # KC with peer destinations: at most 8 peers, and a peer list is required when n_peers > 0
     assert lib.vtm_gather_rows_peers(1, 0, None, 0, 1, 4, 8, None, None, 0.0, 1, 0, None, 1, None) == -1
     arr = (ctypes.c_void_p * 9)(*[ctypes.c_void_p(1)] * 9)

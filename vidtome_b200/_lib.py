@@ -64,6 +64,8 @@ SIGNATURES = {
                                    _vp, _vp, _vp]),
     "vtm_decode_match": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vtm_gather_rows": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _i64, _vp]),
+    "vtm_merge_reduce_workspace_bytes": (_sz, [_i32, _i32, _i32]),
+    "vtm_merge_reduce": (C.c_int, [_vp, _i64, _SPL, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
     "vtm_unmerge_add": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp]),
     "vtm_attention_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "vtm_attention": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, C.c_float, _vp, _vp, _sz, _vp]),

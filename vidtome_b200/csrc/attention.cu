@@ -183,7 +183,7 @@ __device__ __forceinline__ float fa_row_max(const uint32_t (&r)[NCH][32], int n_
 // MUFU 8 (1 - phi) cycles, issue 2.5 + 4 phi slots — balanced near phi = 0.45.  Swept on B200 (tools/sweep_fa_poly.py,
 // ms for qkv + flash + out at B=2, L=10241, 8 heads x 40): see profiles/r02_attention_poly_sweep.md.
 #ifndef VTM_FA_POLY_NUM
-#define VTM_FA_POLY_NUM 7
+#define VTM_FA_POLY_NUM 3
 #endif
 #ifndef VTM_FA_POLY_DEN
 #define VTM_FA_POLY_DEN 16

@@ -7,9 +7,10 @@ C-ABI (K0 normalise+split, KA tcgen05 similarity+arg-max, KB1 stable radix order
 the returned closures are single row-gather kernels over int32 maps instead of chains of
 torch.gather/scatter_ calls on int64 indices expanded to `[b, n, c]`.
 
-Only `merge_mode="replace"` — the only mode any caller in the reference uses (patch.py:45-50,73-75) —
-is implemented; another mode raises NotImplementedError rather than silently doing something else.
-There is no CPU path: tensors must be CUDA fp16.
+`merge_mode="replace"` — the only mode any caller in the reference uses (patch.py:45-50,73-75) — is the composed
+single-gather path; the scatter_reduce modes "mean", "sum", "amax", "amin" (merge.py:126-131) run as an exact,
+order-independent reduction (csrc/reduce.cu); "prod" raises NotImplementedError rather than silently doing something
+else.  There is no CPU path: tensors must be CUDA fp16.
 """
 from __future__ import annotations
 
@@ -93,10 +94,10 @@ def _closures(m: LevelMatch, N: int, unmerge_slice: Optional[Tuple[int, int]], m
 
     def merge(x: torch.Tensor, mode=None) -> torch.Tensor:
         mode = mode if mode is not None else merge_mode
-        if mode != "replace":
-            raise NotImplementedError(
-                f"vidtome_b200: merge mode {mode!r} is not implemented (the reference never uses it)")
         _check_metric(x)
+        if mode != "replace":
+            # merge.py:126-131: scatter_reduce of the matched src rows into their dst rows (include_self=True)
+            return ops.merge_reduce(x.contiguous(), m.split, m.r, m.keys, m.edge, mode)
         return ops.gather_rows(x.contiguous(), mu)               # merge.py:119-133, one pass
 
     def unmerge(x: torch.Tensor, **kwarg) -> torch.Tensor:

@@ -225,6 +225,28 @@ def gather_rows_peers(x: torch.Tensor, row_map: Optional[torch.Tensor], out: tor
     return out
 
 
+MERGE_MODES = {"mean": 1, "sum": 2, "amax": 3, "amin": 4}
+
+
+def merge_reduce(x: torch.Tensor, split: VtmSplit, r: int, keys: torch.Tensor, edge: torch.Tensor, mode: str) -> torch.Tensor:
+    """merge(x, mode) for the scatter_reduce modes (merge.py:126-131): [unmerged src | reduce(dst, matched src)]."""
+    _require(x, torch.float16, "x")
+    if mode not in MERGE_MODES:
+        raise NotImplementedError(f"vidtome_b200: merge mode {mode!r} is not implemented (replace, mean, sum, amax, amin are)")
+    B, _, Cc = x.shape
+    ns, nd = split_counts(split)
+    Bp = keys.shape[0]
+    lib = _lib.load()
+    ws_bytes = lib.vtm_merge_reduce_workspace_bytes(B, nd, Cc)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    y = torch.empty((B, ns - r + nd, Cc), dtype=torch.float16, device=x.device)
+    kp, ep = (None, None) if ns == 0 else (keys.data_ptr(), edge.data_ptr())
+    check(lib.vtm_merge_reduce(x.data_ptr(), x.stride(0), C.byref(split), r, Bp, kp, ep, B, Cc, MERGE_MODES[mode],
+                               y.data_ptr(), ws.data_ptr(), ws_bytes, _stream()), "vtm_merge_reduce")
+    STATS.launches += 3
+    return y
+
+
 def unmerge_add(y: torch.Tensor, row_map: torch.Tensor, resid: Optional[torch.Tensor]) -> torch.Tensor:
     """KE.  out[b, p] = y[b, map[b, p]] (+ resid[b, p]).  y [B, L, C]; map [B'|1, N] int32; resid [B, N, C]."""
     _require(y, torch.float16, "y")
