@@ -68,10 +68,12 @@ def child():
 def main():
     vdir = os.path.join(ROOT, "build", "variants")
     names = ["default"] + sorted(n for n in os.listdir(vdir) if os.path.exists(os.path.join(vdir, n, "libvidtome_b200.so"))) if os.path.isdir(vdir) else ["default"]
-    for n in names:
-        env = dict(os.environ, VTM_VARIANT=n)
-        if n != "default":
-            env["VIDTOME_B200_LIB"] = os.path.join(vdir, n, "libvidtome_b200.so")
+    runs = [(n, {}) for n in names] + [(n + "_2cta_per_sm", {"VTM_FA_GROUPS": "0"}) for n in names if n in ("default", "poly00")]
+    for n, extra in runs:
+        env = dict(os.environ, VTM_VARIANT=n, **extra)
+        base = n.replace("_2cta_per_sm", "")
+        if base != "default":
+            env["VIDTOME_B200_LIB"] = os.path.join(vdir, base, "libvidtome_b200.so")
         subprocess.run([sys.executable, os.path.abspath(__file__), "--child"], env=env, check=False)
 
 

@@ -554,15 +554,41 @@ __global__ void fa_combine_kernel(const FaParams p, int dv_n, int n_split_tiles)
   *reinterpret_cast<uint4*>(p.o + (static_cast<size_t>(b) * p.L + row) * p.C + h * p.d + g * 8) = v;
 }
 
+}  // namespace
+}  // namespace vtm
+#include "attention_groups.cuh"
+namespace vtm {
+namespace {
+
 // Upper bound on split units (remainder tiles x splits); sizes the partial buffers in the workspace.
 constexpr int FA_MAX_SPLIT_UNITS = 320;
 constexpr int FA_MAX_SPLITS = 8;
 constexpr size_t FA_PART_BYTES = static_cast<size_t>(FA_MAX_SPLIT_UNITS) * BQ * (128 * sizeof(float) + sizeof(float2));
 
+// Which flash kernel: the grouped one (attention_groups.cuh: one CTA per SM, G softmax groups) unless VTM_FA_GROUPS=0
+// asks for the two-CTAs-per-SM kernel above (A/B measurements).  Read once; immutable afterwards.
+bool fa_use_groups() {
+  static const int v = [] {
+    const char* e = getenv("VTM_FA_GROUPS");
+    return (e && e[0] == '0') ? 0 : 1;
+  }();
+  return v != 0;
+}
+int fa_forced_splits() {
+  static const int v = [] {
+    const char* e = getenv("VTM_FA_SPLITS");   // tuning override (tools/sweep_fa_splits.py)
+    return e ? atoi(e) : 0;
+  }();
+  return v;
+}
+
 template <int KSTEPS, bool ONES>
 int launch_fa_impl(const void* qkvh, __half* o, void* part_ws, int B, int L, int C, int H, int d, float scale,
               cudaStream_t stream) {
   using Cf = FaCfg<KSTEPS>;
+  using Cg = FaGCfg<KSTEPS>;
+  const bool groups = fa_use_groups();
+  const int bkv = groups ? Cg::BKV : Cf::BKV;
   CUtensorMap tq, tk, tv;
   const int DP = Cf::ATOMS * 64;                       // padded head_dim of the head-major q/k/v buffers
   const uint64_t BH = static_cast<uint64_t>(B) * H;
@@ -570,20 +596,28 @@ int launch_fa_impl(const void* qkvh, __half* o, void* part_ws, int B, int L, int
   const uint64_t which_stride = BH * L * DP;
   int rc = make_tmap_3d_f16(&tq, base, DP, L, BH, DP, static_cast<uint64_t>(L) * DP, 64, BQ);
   if (rc) return rc;
-  rc = make_tmap_3d_f16(&tk, base + which_stride, DP, L, BH, DP, static_cast<uint64_t>(L) * DP, 64, Cf::BKV);
+  rc = make_tmap_3d_f16(&tk, base + which_stride, DP, L, BH, DP, static_cast<uint64_t>(L) * DP, 64, bkv);
   if (rc) return rc;
-  rc = make_tmap_3d_f16(&tv, base + 2 * which_stride, DP, L, BH, DP, static_cast<uint64_t>(L) * DP, 64, Cf::BKV);
+  rc = make_tmap_3d_f16(&tv, base + 2 * which_stride, DP, L, BH, DP, static_cast<uint64_t>(L) * DP, 64, bkv);
   if (rc) return rc;
-  rc = cuda_rc(cudaFuncSetAttribute(flash_attn_kernel<KSTEPS, ONES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(Cf::SMEM_BYTES)));
-  if (rc) return rc;
-  int sms = 0, per_sm = 0;
+  int sms = 0, per_sm = 1;
   rc = gemm::device_sms(&sms);
   if (rc) return rc;
-  rc = cuda_rc(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flash_attn_kernel<KSTEPS, ONES>, FA_THREADS,
-                                                             Cf::SMEM_BYTES));
-  if (rc) return rc;
-  const int slots = sms * (per_sm > 0 ? per_sm : 1);
+  // one-time per instantiation: shared-memory opt-in and occupancy (immutable afterwards)
+  static int attr_rc = -1, occ = 0;
+  if (attr_rc != 0) {
+    attr_rc = cuda_rc(cudaFuncSetAttribute(flash_attn_kernel<KSTEPS, ONES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(Cf::SMEM_BYTES)));
+    if (attr_rc) return attr_rc;
+    attr_rc = cuda_rc(cudaFuncSetAttribute(flash_attn_groups_kernel<KSTEPS, ONES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(Cg::SMEM_BYTES)));
+    if (attr_rc) return attr_rc;
+    attr_rc = cuda_rc(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, flash_attn_kernel<KSTEPS, ONES>, FA_THREADS,
+                                                                    Cf::SMEM_BYTES));
+    if (attr_rc) return attr_rc;
+  }
+  per_sm = groups ? 1 : (occ > 0 ? occ : 1);
+  const int slots = sms * per_sm;
 
   FaParams p;
   p.L = L; p.H = H; p.d = d; p.C = C;
@@ -594,11 +628,11 @@ int launch_fa_impl(const void* qkvh, __half* o, void* part_ws, int B, int L, int
   // the GPU idle for a whole tile time.  The tiles of that wave are cut into `splits` key ranges instead (chosen to
   // minimise the time of the remainder, ceil(R * S / slots) / S tile times) and merged by fa_combine_kernel.
   const long long tiles = static_cast<long long>(p.n_qtiles) * H * B;
-  const int nkv = (L + Cf::BKV - 1) / Cf::BKV;
+  const int nkv = (L + bkv - 1) / bkv;
   const int rem = static_cast<int>(tiles % slots);
   int splits = 1;
   if (rem > 0) {
-    // Time of the remainder in tile times.  The kernel is bound by per-SM throughput (MUFU), so what counts is the
+    // Time of the remainder in tile times.  The kernel is bound by per-SM throughput, so what counts is the
     // number of units the busiest SM gets, not CTA slots: sub-waves over `sms` x (1 / S + fixed cost of a unit,
     // about four key tiles).  Split only for a clear gain (the merge is one more launch).
     const double fixed = 4.0 / nkv;
@@ -608,8 +642,7 @@ int launch_fa_impl(const void* qkvh, __half* o, void* part_ws, int B, int L, int
       if (t < best_t - 1e-9) { best_t = t; splits = sp; }
     }
   }
-  if (const char* e = getenv("VTM_FA_SPLITS")) {   // tuning override (tools/sweep_fa_splits.py)
-    const int sp = atoi(e);
+  if (const int sp = fa_forced_splits()) {
     if (sp >= 1 && sp <= FA_MAX_SPLITS && sp <= nkv && static_cast<long long>(rem) * sp <= FA_MAX_SPLIT_UNITS)
       splits = rem > 0 ? sp : 1;
   }
@@ -619,7 +652,10 @@ int launch_fa_impl(const void* qkvh, __half* o, void* part_ws, int B, int L, int
   p.part_o = reinterpret_cast<float*>(static_cast<char*>(part_ws) +
                                       static_cast<size_t>(FA_MAX_SPLIT_UNITS) * BQ * sizeof(float2));
   const long long units = p.n_full + (tiles - p.n_full) * splits;
-  flash_attn_kernel<KSTEPS, ONES><<<static_cast<unsigned>(units), FA_THREADS, Cf::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  if (groups)
+    flash_attn_groups_kernel<KSTEPS, ONES><<<static_cast<unsigned>(units), Cg::THREADS, Cg::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  else
+    flash_attn_kernel<KSTEPS, ONES><<<static_cast<unsigned>(units), FA_THREADS, Cf::SMEM_BYTES, stream>>>(tq, tk, tv, p);
   rc = launch_rc();
   if (rc || splits == 1) return rc;
   const long long work = static_cast<long long>(rem) * BQ * (d / 8);
