@@ -308,6 +308,52 @@ def comparators(torch, net, dev, steps, kind):
     return out
 
 
+def c4_global_block(torch, dist, dev, rank, world, steps, timed):
+    """BASELINE config 4 (secondary block, `--c4-global`, N > 1): SD2.1-shaped skeleton at 768^2 (latent 96x96), one
+    8-frame chunk per GPU, local 0.9 + GLOBAL 0.8 merging with the global-token set exchanged once per merged block
+    (SURVEY §8e option A: rank k matches against the merged tokens of rank k-1), in both exchange modes."""
+    import vidtome_b200
+    from vidtome_b200 import ops, patch
+    from vidtome_b200.driver import ChunkedDenoiser
+    from vidtome_b200.skeleton import make_skeleton
+    torch.manual_seed(123)
+    net = make_skeleton("sd21", hot_path_only=True, device=dev)
+    vidtome_b200.apply_patch(net, local_merge_ratio=RATIO, batch_size=2, merge_global=True, global_merge_ratio=0.8)
+    g = torch.Generator(device=dev).manual_seed(900 + rank)
+    x0 = torch.randn((8, 4, 96, 96), generator=g, device=dev, dtype=torch.float16)
+    res = {"workload": "sd21_768_f8_chunk_per_gpu_local0.9_global0.8", "chunks": world, "frames_per_chunk": 8,
+           "latent": [4, 96, 96], "exchange": {}}
+    n = max(2, min(steps, 5))
+    for mode in ("allgather", "p2p"):
+        patch.GLOBAL_EXCHANGE = mode
+        try:
+            den = ChunkedDenoiser(net, n_timesteps=50, chunk_size=8, merge_global=True)
+            st = {"x": x0.clone()}
+
+            def step(i):
+                st["x"] = den.step(st["x"], i % 50)
+            for i in range(2):
+                step(i)
+            ops.STATS.reset(timed=("KF",))
+            ms = timed(step, n)
+            ev = ops.STATS.events.get("KF", [])
+            kf_ms = sum(s.elapsed_time(e) for s, e, _, _ in ev)
+            kf_bytes = sum(b for _, _, _, b in ev)
+            ops.STATS.reset()
+            t = torch.tensor([kf_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            res["exchange"][mode] = {"ms_per_step": round(ms / n, 3), "steps_per_s_all_ranks": round(world * n / (ms / 1e3), 3),
+                                     "merge_gather_plus_exchange_ms_per_step": round(float(t.item()) / n, 4),
+                                     "exchanges_per_step": len(ev) // n,
+                                     "nvlink_bytes_per_rank_per_step": int(kf_bytes / n),
+                                     "nvlink_GBs_per_rank_within_exchange": round(kf_bytes / max(kf_ms, 1e-9) / 1e6, 1)}
+        except Exception as exc:                      # reported, never fatal for the headline line
+            res["exchange"][mode] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+    patch.GLOBAL_EXCHANGE = "recurrence"
+    vidtome_b200.remove_patch(net)
+    return res
+
+
 # ------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -394,6 +440,10 @@ def run_ours(args):
     events = dict(ops.STATS.events)
     ops.STATS.reset()
 
+    c4 = None
+    if world > 1 and args.c4_global:
+        c4 = c4_global_block(torch, dist, dev, rank, world, args.steps, timed)
+
     if rank == 0:
         pk = peaks()
 
@@ -450,6 +500,8 @@ def run_ours(args):
             "roofline": roof,
             "rooflines": others,
         }
+        if c4 is not None:
+            out["c4_global"] = c4
         if world == 1 and not args.no_gpu_ref:
             vidtome_b200.remove_patch(net)
             out["comparators"] = comparators(torch, net, dev, args.steps, kind)
@@ -484,6 +536,8 @@ def main():
     ap.add_argument("--no-numpy", action="store_true", help="skip the numpy-oracle second CPU figure")
     ap.add_argument("--no-gpu-ref", action="store_true", help="skip the same-GPU comparators")
     ap.add_argument("--e2e-eager", action="store_true", help="end-to-end leg without CUDA-graph replay")
+    ap.add_argument("--c4-global", action="store_true",
+                    help="N > 1 only: append BASELINE config 4 with the global-token exchange (all-gather and fused p2p)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -238,6 +238,22 @@ int vtm_attention(const void* x_dev, const void* w_qkv_dev, const void* w_o_dev,
 int vtm_linear_f16(const void* a_dev, const void* w_dev, const void* bias_dev, int32_t M, int32_t N,
                    int32_t K, void* d_dev, int64_t ldd, void* stream);
 
+/*
+ * Feed-forward of the patched block (vidtome/patch.py:187-199 calls `self.ff(norm3(h))` and adds the residual; the
+ * module is diffusers' FeedForward = GEGLU(dim -> 4 dim) -> Dropout -> Linear(4 dim -> dim)) on tcgen05:
+ *
+ * vtm_linear_geglu_f16:  D[M, N/2] = h * gelu(gate) with [h | gate] = A[M, K] * W^T + bias (erf form of gelu, torch's
+ *   F.gelu default).  `w_il_dev` [N, K] and `bias_il_dev` [N] hold the projection's rows INTERLEAVED in groups of 32:
+ *   rows [64 q, 64 q + 32) = rows [32 q, 32 q + 32) of the value half, rows [64 q + 32, 64 q + 64) = the same rows of the
+ *   gate half (so that a value and its gate land in one 64-column TMEM load).  N % 64 == 0.  Roundings follow torch's
+ *   fp16 pipeline: projection -> fp16, gelu(gate) -> fp16, product -> fp16.
+ * vtm_linear_residual_f16:  D[M, N] = fp16(fp16(A W^T + bias) + resid[M, N]) — `lin(x) + hidden_states`.
+ */
+int vtm_linear_geglu_f16(const void* a_dev, const void* w_il_dev, const void* bias_il_dev, int32_t M, int32_t N,
+                         int32_t K, void* d_dev, int64_t ldd, void* stream);
+int vtm_linear_residual_f16(const void* a_dev, const void* w_dev, const void* bias_dev, const void* resid_dev,
+                            int64_t ldr, int32_t M, int32_t N, int32_t K, void* d_dev, int64_t ldd, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

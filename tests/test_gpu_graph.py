@@ -91,3 +91,21 @@ def test_device_resident_randf_matches_host_randf():
         assert torch.equal(mu0, mu1) and torch.equal(pi0, pi1)
     with pytest.raises(RuntimeError):          # 6 frames, stride 4: counts would depend on the draw
         ops.split_counts(VtmSplit.local(6 * T, 0, 6, 4, torch.tensor([1], device="cuda", dtype=torch.int32)))
+
+
+def test_two_gpu_global_exchange_bit_exact():
+    """§8e on hardware: chunk-per-GPU global merging on 2 ranks (NCCL): the all-gather exchange and the exchange fused
+    into the merge gather (peer stores over NVLink) both reproduce, bit for bit, the single-GPU computation fed the
+    same global tokens (tools/check_dist_gpu.py).  Needs two GPUs on the box; skipped otherwise."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29641", os.path.join(root, "tools", "check_dist_gpu.py")],
+                       capture_output=True, text=True, timeout=600)
+    print(r.stdout[-2000:])
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert "allgather bit-exact=True" in r.stdout and "fused-p2p bit-exact=True" in r.stdout

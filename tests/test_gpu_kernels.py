@@ -304,3 +304,86 @@ def test_fused_layernorm_in_k0_and_kc(C):
     m1 = ops.gather_rows(x, mu, ln=(ln.weight.data, ln.bias.data, ln.eps))
     d = _ulp_diff_f16(m1.cpu().numpy(), m0.cpu().numpy())
     assert d.max() <= 1 and (d > 0).mean() < 0.01
+
+
+# --------------------------------------------------------------------------- feed-forward GEMMs (f3)
+@pytest.mark.parametrize("M,K,inner", [(256, 64, 128), (1000, 320, 1280), (4099, 640, 2560)])
+def test_linear_geglu_and_residual(M, K, inner):
+    """GEGLU projection with the gate fused into the epilogue, and the output projection with bias + residual, against
+    the unfused fp16 torch ops (F.linear -> chunk -> a * gelu(g); F.linear + h): same rounding points, so agreement is
+    at the level of one fp16 ulp of the result."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(M)
+    a = torch.randn((M, K), generator=g, device="cuda").half()
+    w = (torch.randn((2 * inner, K), generator=g, device="cuda") / K ** 0.5).half()
+    b = (0.1 * torch.randn((2 * inner,), generator=g, device="cuda")).half()
+    wi, bi = ops.interleave_geglu(w, b)
+    u = ops.linear_geglu(a, wi, bi)
+    proj = torch.nn.functional.linear(a, w, b)
+    h, gate = proj.chunk(2, dim=-1)
+    want = h * torch.nn.functional.gelu(gate)
+    ref32 = (a.float() @ w.float().t() + b.float())
+    r_h, r_g = ref32.chunk(2, dim=-1)
+    ref = r_h * torch.nn.functional.gelu(r_g)
+    scale = ref.abs().max().item()
+    assert (u.float() - ref).abs().max().item() <= 2e-3 * scale            # vs exact arithmetic
+    assert (u.float() - want.float()).abs().max().item() <= 2e-3 * scale   # vs torch's fp16 pipeline
+    w2 = (torch.randn((K, inner), generator=g, device="cuda") / inner ** 0.5).half()
+    b2 = (0.1 * torch.randn((K,), generator=g, device="cuda")).half()
+    resid = torch.randn((M, K), generator=g, device="cuda").half()
+    out = ops.linear_residual(u, w2, b2, resid)
+    want2 = torch.nn.functional.linear(u, w2, b2) + resid
+    ref2 = u.float() @ w2.float().t() + b2.float() + resid.float()
+    s2 = ref2.abs().max().item()
+    assert (out.float() - ref2).abs().max().item() <= 2e-3 * s2
+    assert (out.float() - want2.float()).abs().max().item() <= 2e-3 * s2
+
+
+def test_feed_forward_fast_path_matches_module():
+    """feedforward.feed_forward_residual == h + ff(norm3(h)) of the module (both stand-in layouts: the skeleton's
+    GEGLUFeedForward and diffusers' FeedForward.net = [GEGLU, Dropout, Linear])."""
+    from vidtome_b200 import feedforward, patch
+    from vidtome_b200.skeleton import GEGLUFeedForward
+    torch.manual_seed(0)
+    dim = 320
+
+    class GEGLU(torch.nn.Module):
+        def __init__(self, dim_in, dim_out):
+            super().__init__()
+            self.proj = torch.nn.Linear(dim_in, dim_out * 2)
+
+        def forward(self, x):
+            h, gate = self.proj(x).chunk(2, dim=-1)
+            return h * torch.nn.functional.gelu(gate)
+
+    class FeedForward(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.net = torch.nn.ModuleList([GEGLU(dim, 4 * dim), torch.nn.Dropout(0.0), torch.nn.Linear(4 * dim, dim)])
+
+        def forward(self, x):
+            for m in self.net:
+                x = m(x)
+            return x
+
+    for ff in (GEGLUFeedForward(dim), FeedForward()):
+        ff = ff.cuda().half().eval()
+        norm = torch.nn.LayerNorm(dim).cuda().half()
+        with torch.no_grad():
+            norm.weight.add_(0.1 * torch.randn_like(norm.weight))
+            norm.bias.add_(0.1 * torch.randn_like(norm.bias))
+        h = torch.randn((6, 500, dim), device="cuda").half()
+        parts = feedforward.geglu_parts(ff)
+        assert parts is not None
+        ln = patch._fusable_layer_norm(norm, h)
+        with torch.no_grad():
+            got = feedforward.feed_forward_residual(ff, parts, ln, h)
+            want = ff(norm(h)) + h
+            ref = ff.float()(norm.float()(h.float())) + h.float()
+        s = ref.abs().max().item()
+        assert (got.float() - ref).abs().max().item() <= 2e-3 * s
+        assert (got.float() - want.float()).abs().max().item() <= 3e-3 * s
+    # anything non-stock is refused
+    ff = GEGLUFeedForward(dim).cuda().half()
+    ff.register_forward_hook(lambda m, i, o: o)
+    assert feedforward.geglu_parts(ff) is None

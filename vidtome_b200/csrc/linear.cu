@@ -11,7 +11,8 @@ struct StoreEpi {
   static constexpr uint32_t SCRATCH_PER_WARP = gemm::STAGE_STORE_BYTES;
   __half* d;
   const __half* bias;
-  long long ldd;
+  const __half* resid;   // optional [M, N] (row stride ldr): D = fp16(fp16(acc + bias) + resid), torch's `lin(x) + h`
+  long long ldd, ldr;
   int M, N;
   int row0;            // first of the warp's 32 rows
   uint32_t scratch;
@@ -41,9 +42,97 @@ struct StoreEpi {
       const int c = c0 + (threadIdx.x & 7) * 8;
       int row = row0 + ((threadIdx.x & 31) >> 3);
       __half* dst = d + static_cast<long long>(row) * ldd + c;
-      const long long row_step = 4 * ldd;
+      const __half* rs = resid ? resid + static_cast<long long>(row) * ldr + c : nullptr;
+      const long long row_step = 4 * ldd, rrow_step = 4 * ldr;
       gemm::warp_store_rows64(scratch, pk, [&](int, int, const uint4& v) {
-        if (row < M && c < N) *reinterpret_cast<uint4*>(dst) = v;
+        if (row < M && c < N) {
+          uint4 o = v;
+          if (rs) {
+            const uint4 rv = *reinterpret_cast<const uint4*>(rs);
+            __half2* a = reinterpret_cast<__half2*>(&o);
+            const __half2* b2 = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) a[e] = __hadd2(a[e], b2[e]);
+          }
+          *reinterpret_cast<uint4*>(dst) = o;
+        }
+        row += 4;
+        dst += row_step;
+        if (rs) rs += rrow_step;
+      });
+    }
+  }
+  __device__ __forceinline__ void end(int, int, int) {}
+};
+
+// erf via Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below fp16 resolution): two MUFU ops + 8 FMA-pipe ops.
+__device__ __forceinline__ float erf_as(float x) {
+  const float ax = fabsf(x);
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  const float e = ex2_approx(-1.4426950408889634f * ax * ax);
+  return copysignf(fmaf(-p, e, 1.f), x);
+}
+
+// GEGLU epilogue (diffusers GEGLU: `h, gate = proj(x).chunk(2, -1); h * gelu(gate)`, the first layer of the
+// feed-forward the reference block calls at vidtome/patch.py:187-199).  The weight rows are interleaved on the host in
+// groups of 32 ([a 0..31 | gate 0..31 | a 32..63 | gate 32..63 | ...]) so that an epilogue thread finds a value and its
+// gate in the same 64-column TMEM load; the output has N/2 columns.  Roundings follow torch's fp16 pipeline: proj output
+// -> fp16, gelu(gate) (erf form, evaluated in fp32) -> fp16, product -> fp16.
+struct GegluEpi {
+  static constexpr uint32_t SCRATCH_PER_WARP = gemm::STAGE_STORE_BYTES;
+  __half* d;             // [M, N/2]
+  const __half* bias;    // [N], interleaved like the weight rows (may be null)
+  long long ldd;
+  int M, N;              // N = GEMM width (2 x output width), N % 64 == 0
+  int row0;
+  uint32_t scratch;
+
+  __device__ __forceinline__ void set_scratch(uint32_t a) { scratch = a; }
+  __device__ __forceinline__ void begin(int m_tile, int, int row_in_tile) {
+    row0 = m_tile * gemm::BM + (row_in_tile & ~31);
+  }
+  __device__ __forceinline__ void tile(uint32_t taddr, int col0, int ncols) {
+    // two 64-column loads ([a32|g32] twice) give 64 outputs = one staged store of 32 rows x 64 columns
+#pragma unroll 1
+    for (int cb = 0; cb < ncols; cb += 128) {
+      uint32_t pk[32];
+#pragma unroll
+      for (int hlf = 0; hlf < 2; ++hlf) {
+        uint32_t r[64];
+        tmem_ld_32x32b_x64(taddr + cb + 64 * hlf, r);
+        tmem_ld_wait();
+        const int c0 = col0 + cb + 64 * hlf;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          float a0 = __uint_as_float(r[2 * e]), a1 = __uint_as_float(r[2 * e + 1]);
+          float g0 = __uint_as_float(r[32 + 2 * e]), g1 = __uint_as_float(r[32 + 2 * e + 1]);
+          if (bias && c0 < N) {
+            a0 += __half2float(bias[c0 + 2 * e]);
+            a1 += __half2float(bias[c0 + 2 * e + 1]);
+            g0 += __half2float(bias[c0 + 32 + 2 * e]);
+            g1 += __half2float(bias[c0 + 32 + 2 * e + 1]);
+          }
+          // fp16 roundings of the unfused pipeline
+          a0 = __half2float(__float2half_rn(a0)); a1 = __half2float(__float2half_rn(a1));
+          g0 = __half2float(__float2half_rn(g0)); g1 = __half2float(__float2half_rn(g1));
+          const float q0 = __half2float(__float2half_rn(0.5f * g0 * (1.f + erf_as(g0 * 0.7071067811865476f))));
+          const float q1 = __half2float(__float2half_rn(0.5f * g1 * (1.f + erf_as(g1 * 0.7071067811865476f))));
+          pk[16 * hlf + e] = pack_f16x2(a0 * q0, a1 * q1);
+        }
+      }
+      const int oc0 = (col0 + cb) >> 1;                       // first output column of this 64-wide store
+      const int c = oc0 + (threadIdx.x & 7) * 8;
+      int row = row0 + ((threadIdx.x & 31) >> 3);
+      __half* dst = d + static_cast<long long>(row) * ldd + c;
+      const long long row_step = 4 * ldd;
+      const int No = N >> 1;
+      gemm::warp_store_rows64(scratch, pk, [&](int, int, const uint4& v) {
+        if (row < M && c < No) *reinterpret_cast<uint4*>(dst) = v;
         row += 4;
         dst += row_step;
       });
@@ -55,20 +144,21 @@ struct StoreEpi {
 }  // namespace
 }  // namespace vtm
 
-extern "C" int vtm_linear_f16(const void* a_dev, const void* w_dev, const void* bias_dev, int32_t M, int32_t N,
-                              int32_t K, void* d_dev, int64_t ldd, void* stream_) {
-  using namespace vtm;
+namespace vtm {
+namespace {
+int linear_impl(const void* a_dev, const void* w_dev, const void* bias_dev, const void* resid_dev, long long ldr,
+                int M, int N, int K, void* d_dev, long long ldd, cudaStream_t stream) {
   if (!a_dev || !w_dev || !d_dev) return VTM_E_NULL;
-  if (M <= 0 || N <= 0 || K <= 0 || (K % 8) != 0 || (N % 8) != 0 || (ldd % 8) != 0 || ldd < N)
-    return VTM_E_SHAPE;
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (M <= 0 || N <= 0 || K <= 0 || (K % 8) != 0 || (N % 8) != 0 || (ldd % 8) != 0 || ldd < N) return VTM_E_SHAPE;
+  if (resid_dev && ((ldr % 8) != 0 || ldr < N)) return VTM_E_SHAPE;
   int sms = 0;
   int rc = gemm::device_sms(&sms);
   if (rc) return rc;
   StoreEpi epi;
   epi.d = static_cast<__half*>(d_dev);
   epi.bias = static_cast<const __half*>(bias_dev);
-  epi.ldd = ldd; epi.M = M; epi.N = N; epi.row0 = 0; epi.scratch = 0;
+  epi.resid = static_cast<const __half*>(resid_dev);
+  epi.ldd = ldd; epi.ldr = ldr; epi.M = M; epi.N = N; epi.row0 = 0; epi.scratch = 0;
   CUtensorMap ta, tb;
   rc = make_tmap_3d_f16(&ta, a_dev, K, M, 1, K, static_cast<uint64_t>(M) * K, gemm::BK, gemm::BM);
   if (rc) return rc;
@@ -85,4 +175,41 @@ extern "C" int vtm_linear_f16(const void* a_dev, const void* w_dev, const void* 
   if (rc) return rc;
   wk.plan(M, N, K, 1, 128, sms, 16, 1);
   return gemm::launch<128, StoreEpi>(ta, tb, wk, epi, sms, stream);
+}
+}  // namespace
+}  // namespace vtm
+
+extern "C" int vtm_linear_f16(const void* a_dev, const void* w_dev, const void* bias_dev, int32_t M, int32_t N,
+                              int32_t K, void* d_dev, int64_t ldd, void* stream_) {
+  return vtm::linear_impl(a_dev, w_dev, bias_dev, nullptr, 0, M, N, K, d_dev, ldd, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int vtm_linear_residual_f16(const void* a_dev, const void* w_dev, const void* bias_dev, const void* resid_dev,
+                                       int64_t ldr, int32_t M, int32_t N, int32_t K, void* d_dev, int64_t ldd,
+                                       void* stream_) {
+  if (!resid_dev) return VTM_E_NULL;
+  return vtm::linear_impl(a_dev, w_dev, bias_dev, resid_dev, ldr, M, N, K, d_dev, ldd, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int vtm_linear_geglu_f16(const void* a_dev, const void* w_il_dev, const void* bias_il_dev, int32_t M,
+                                    int32_t N, int32_t K, void* d_dev, int64_t ldd, void* stream_) {
+  using namespace vtm;
+  if (!a_dev || !w_il_dev || !d_dev) return VTM_E_NULL;
+  if (M <= 0 || N <= 0 || K <= 0 || (K % 8) != 0 || (N % 64) != 0 || (ldd % 8) != 0 || ldd < N / 2) return VTM_E_SHAPE;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int sms = 0;
+  int rc = gemm::device_sms(&sms);
+  if (rc) return rc;
+  GegluEpi epi;
+  epi.d = static_cast<__half*>(d_dev);
+  epi.bias = static_cast<const __half*>(bias_il_dev);
+  epi.ldd = ldd; epi.M = M; epi.N = N; epi.row0 = 0; epi.scratch = 0;
+  CUtensorMap ta, tb;
+  rc = make_tmap_3d_f16(&ta, a_dev, K, M, 1, K, static_cast<uint64_t>(M) * K, gemm::BK, gemm::BM);
+  if (rc) return rc;
+  rc = make_tmap_3d_f16(&tb, w_il_dev, K, N, 1, K, static_cast<uint64_t>(N) * K, gemm::BK, 256);
+  if (rc) return rc;
+  gemm::Work wk;
+  wk.plan(M, N, K, 1, 256, sms, 16, 1);
+  return gemm::launch<256, GegluEpi>(ta, tb, wk, epi, sms, stream);
 }

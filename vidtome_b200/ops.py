@@ -281,6 +281,60 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     return d
 
 
+def linear_residual(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], resid: torch.Tensor) -> torch.Tensor:
+    """D = (A W^T + bias) + resid, with torch's fp16 roundings (`lin(x) + h`).  a [M, K], w [N, K], resid [M, N]."""
+    _require(a, torch.float16, "a")
+    _require(w, torch.float16, "w")
+    _require(resid, torch.float16, "resid")
+    M, K = a.shape
+    N = w.shape[0]
+    if tuple(resid.shape) != (M, N):
+        raise RuntimeError("linear_residual: resid must be [M, N]")
+    d = torch.empty((M, N), dtype=torch.float16, device=a.device)
+    if bias is not None:
+        _require(bias, torch.float16, "bias")
+    with _Timed("FF2", 2.0 * M * N * K, 2.0 * (M * K + N * K + 2 * M * N)):
+        check(_lib.load().vtm_linear_residual_f16(a.data_ptr(), w.data_ptr(), _ptr(bias), resid.data_ptr(), N, M, N, K,
+                                                  d.data_ptr(), N, _stream()), "vtm_linear_residual_f16")
+    STATS.launches += 1
+    return d
+
+
+def interleave_geglu(w: torch.Tensor, bias: Optional[torch.Tensor]):
+    """Row order vtm_linear_geglu_f16 expects: groups of 32 value rows followed by their 32 gate rows."""
+    N, K = w.shape
+    No = N // 2
+    if No % 32 != 0:
+        raise RuntimeError("geglu: inner width must be a multiple of 32")
+    wi = torch.stack([w[:No].reshape(No // 32, 32, K), w[No:].reshape(No // 32, 32, K)], dim=1).reshape(N, K).contiguous()
+    bi = None
+    if bias is not None:
+        bi = torch.stack([bias[:No].reshape(No // 32, 32), bias[No:].reshape(No // 32, 32)], dim=1).reshape(N).contiguous()
+    return wi, bi
+
+
+def linear_geglu(a: torch.Tensor, w_il: torch.Tensor, bias_il: Optional[torch.Tensor]) -> torch.Tensor:
+    """GEGLU projection: [h | gate] = A W^T + b, D = h * gelu(gate).  w_il / bias_il interleaved (interleave_geglu)."""
+    _require(a, torch.float16, "a")
+    _require(w_il, torch.float16, "w_il")
+    M, K = a.shape
+    N = w_il.shape[0]
+    d = torch.empty((M, N // 2), dtype=torch.float16, device=a.device)
+    if bias_il is not None:
+        _require(bias_il, torch.float16, "bias_il")
+    with _Timed("FF1", 2.0 * M * N * K, 2.0 * (M * K + N * K + M * N // 2)):
+        check(_lib.load().vtm_linear_geglu_f16(a.data_ptr(), w_il.data_ptr(), _ptr(bias_il), M, N, K, d.data_ptr(), N // 2,
+                                               _stream()), "vtm_linear_geglu_f16")
+    STATS.launches += 1
+    return d
+
+
+def layer_norm(x: torch.Tensor, ln) -> torch.Tensor:
+    """Plain LayerNorm over the last dim of x [M, C] through the KC kernel with an identity map (torch half semantics)."""
+    M, Cc = x.shape
+    return gather_rows(x.view(1, M, Cc), None, L=M, ln=ln).view(M, Cc)
+
+
 def attention(x: torch.Tensor, w_qkv: torch.Tensor, w_o: torch.Tensor, b_o: Optional[torch.Tensor], heads: int,
               scale: float) -> torch.Tensor:
     """KD.  x [B, L, C] fp16 -> [B, L, C]."""

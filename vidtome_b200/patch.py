@@ -53,6 +53,9 @@ class MergePlan:
 # Fuse a plain nn.LayerNorm norm1 into the K0 / KC kernels (its output is then never materialised).
 FUSE_LAYERNORM = True
 
+# Run a stock GEGLU feed-forward (norm3 + ff + residual, patch.py:187-199) through the tcgen05 kernels (feedforward.py).
+FUSE_FEED_FORWARD = True
+
 # How `merge_global=True` obtains the global token set when several ranks each hold one chunk:
 #   "recurrence" — the reference's semantics (patch.py:59-82): whatever the previous chunk processed by THIS
 #                  process left in module.global_tokens;
@@ -121,12 +124,16 @@ def build_merge_plan(module: torch.nn.Module, x: torch.Tensor, tome_info: Dict[s
         if GLOBAL_EXCHANGE in ("allgather", "p2p"):
             from . import dist as _dist
             if _dist.world() > 1:
-                if GLOBAL_EXCHANGE == "p2p":
-                    # KC stores the merged tokens into every rank's symmetric buffer: no separate collective pass
-                    local_tokens, g = _dist.exchange_fused(table, mu, ln=ln)
-                else:
-                    local_tokens = ops.gather_rows(table, mu, ln=ln)
-                    g = _dist.exchange_global_tokens(local_tokens)          # the one collective of this path
+                # "KF" = the merge gather together with the exchange (bench.py brackets it with CUDA events): bytes that
+                # cross NVLink per rank = (G - 1) * B * L * C * 2 in either mode
+                nvl = 2.0 * (_dist.world() - 1) * B * mu.shape[1] * C
+                with ops._Timed("KF", 0.0, nvl):
+                    if GLOBAL_EXCHANGE == "p2p":
+                        # KC stores the merged tokens into every rank's symmetric buffer: no separate collective pass
+                        local_tokens, g = _dist.exchange_fused(table, mu, ln=ln)
+                    else:
+                        local_tokens = ops.gather_rows(table, mu, ln=ln)
+                        g = _dist.exchange_global_tokens(local_tokens)      # the one collective of this path
                 exchanged = True
         if local_tokens is None:
             local_tokens = ops.gather_rows(table, mu, ln=ln)                 # merged local tokens [B, L, C]
@@ -301,7 +308,15 @@ def make_diffusers_tome_block(block_class: Type[torch.nn.Module]) -> Type[torch.
 
             # 3. Feed-forward (patch.py:187-199).  A block without `ff` (the hot-path skeleton used by
             # bench.py) stops after the self-attention section.
-            if getattr(self, "ff", None) is not None:
+            ff = getattr(self, "ff", None)
+            if ff is not None and FUSE_FEED_FORWARD and hidden_states.is_cuda and not self.use_ada_layer_norm_zero:
+                from . import feedforward as _ff
+                parts = _ff.geglu_parts(ff)
+                ln3 = _fusable_layer_norm(self.norm3, hidden_states) if parts is not None else None
+                if ln3 is not None:
+                    # norm3 -> GEGLU projection (gate fused) -> output projection (+ bias + residual), tcgen05
+                    return _ff.feed_forward_residual(ff, parts, ln3, hidden_states)
+            if ff is not None:
                 norm_hidden_states = self.norm3(hidden_states)
                 if self.use_ada_layer_norm_zero:
                     norm_hidden_states = norm_hidden_states * (1 + scale_mlp[:, None]) + shift_mlp[:, None]
