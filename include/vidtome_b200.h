@@ -232,6 +232,14 @@ int vtm_attention(const void* x_dev, const void* w_qkv_dev, const void* w_o_dev,
                   int32_t B, int32_t L, int32_t C, int32_t heads, float scale, void* y_dev,
                   void* ws_dev, size_t ws_bytes, void* stream);
 
+/* KD with options.  flags bit 0 (VTM_ATTN_SHARED_QK): PnP's source-sample injection (utils/pnp_utils.py:57-68,87-91: the
+ * attention map softmax(q k^T) is computed from sample 0 only and `repeat`ed over the batch): every sample b uses the
+ * queries and keys of sample 0 and its own values.  Other bits must be zero (VTM_E_UNSUPPORTED). */
+#define VTM_ATTN_SHARED_QK 1
+int vtm_attention_ex(const void* x_dev, const void* w_qkv_dev, const void* w_o_dev, const void* b_o_dev,
+                     int32_t B, int32_t L, int32_t C, int32_t heads, float scale, int32_t flags, void* y_dev,
+                     void* ws_dev, size_t ws_bytes, void* stream);
+
 /* Plain tcgen05 GEMM used by KD's projections, exported for tests and the microbench:
  * D[M, N] = A[M, K] * W[N, K]^T (+ bias[N]), fp16 in, fp32 accumulate, fp16 out.  K % 8 == 0,
  * N % 8 == 0; ldd = row stride of D in elements. */

@@ -91,3 +91,60 @@ def test_patched_block_uses_cuda_attention(monkeypatch):
     with torch.no_grad():
         out = net(lat, 0).sample
     assert torch.isfinite(out).all() and not calls
+
+
+def test_pnp_shared_qk_attention_matches_reference_fixture():
+    """f2: PnP's source-sample Q/K injection on merged tokens.  The fixture is the REFERENCE's replaced attn1.forward
+    (utils/pnp_utils.py:39-106) on 3 samples with and without the injection active; here the same module goes through
+    pnp.register_attention_control + KD (vtm_attention_ex, VTM_ATTN_SHARED_QK) and through the torch fallback forward."""
+    import os
+    import numpy as np
+    from vidtome_b200 import attention as A, pnp
+    from vidtome_b200.skeleton import Attention
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pnp_attention_b3.npz"))
+    attn = Attention(int(g["dim"]), int(g["heads"]), int(g["dim"]) // int(g["heads"])).half()
+    attn.load_state_dict({k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd_")})
+    attn = attn.cuda().eval()
+    pnp.register_attention_control(None, [int(v) for v in g["schedule"]], int(g["num_inputs"]), modules=[attn])
+    x = torch.from_numpy(g["x"]).cuda()
+    for t, key in ((981, "out_inject"), (500, "out_plain")):
+        pnp.register_time(None, t, modules=[attn])
+        ref = torch.from_numpy(g[key]).float()
+        scale = ref.abs().max().item()
+        with torch.no_grad():
+            kd = A.self_attention(attn, x, shared_qk=pnp.injection_active(attn)).float().cpu()
+            tf = attn(x).float().cpu()                           # the torch forward installed by pnp.py
+        assert (kd - ref).abs().max().item() <= 1e-3 * scale + 1e-3, key
+        assert (tf - ref).abs().max().item() <= 1e-3 * scale + 1e-3, key
+    assert pnp.injection_active(attn) is False
+
+
+def test_pnp_block_path_uses_kd_with_injection():
+    """A patched block whose attn1 carries pnp.py's control runs KD with the shared attention map while the timestep is
+    in the schedule: equal to the torch forward of the same module on the block's merged tokens."""
+    import vidtome_b200
+    from vidtome_b200 import patch, pnp
+    from vidtome_b200.skeleton import make_skeleton
+    net = make_skeleton("tiny", device="cuda", max_downsample=1, seed=3)
+    vidtome_b200.apply_patch(net, batch_size=3, local_merge_ratio=0.9, align_batch=True)
+    mods = [b.attn1 for b in net.blocks]
+    pnp.register_attention_control(net, [981], 3, modules=mods)
+    pnp.register_time(net, 981)
+    assert all(patch._plain_attention_module(m) for m in mods)
+    torch.manual_seed(1)
+    lat = torch.randn(3 * 4, 4, 16, 16, device="cuda", dtype=torch.float16)
+    outs = []
+    for kd in (True, False):
+        from vidtome_b200 import attention as A
+        A.ENABLED = kd
+        try:
+            torch.manual_seed(5); torch.cuda.manual_seed(5)
+            for b in net.blocks:
+                if hasattr(b, "generator"):
+                    del b.generator
+            with torch.no_grad():
+                outs.append(net(lat, 0).sample.float())
+        finally:
+            A.ENABLED = True
+    err = (outs[0] - outs[1]).abs().max().item()
+    assert err <= 2e-3 * outs[1].abs().max().item() + 1e-3

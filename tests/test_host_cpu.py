@@ -362,3 +362,23 @@ def test_kd_fast_path_only_for_stock_attention_modules():
     assert not patch._plain_attention_module(a)
     a = fresh(); a.to_k = torch.nn.Linear(64, 64, bias=True)
     assert not patch._plain_attention_module(a)
+
+
+def test_pnp_torch_forward_equals_reference_fixture_on_cpu():
+    """pnp.register_attention_control installs a forward that IS the reference's PnP forward (utils/pnp_utils.py:47-95):
+    bit-identical to the fixture the reference produced (tests/make_golden_r02.py --pnp), injection on and off."""
+    from vidtome_b200 import patch, pnp
+    from vidtome_b200.skeleton import Attention
+    g = np.load(os.path.join(ROOT, "tests", "golden", "pnp_attention_b3.npz"))
+    attn = Attention(int(g["dim"]), int(g["heads"]), int(g["dim"]) // int(g["heads"])).half()
+    attn.load_state_dict({k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd_")})
+    pnp.register_attention_control(None, [981, 961], 3, modules=[attn])
+    x = torch.from_numpy(g["x"])
+    for t, key in ((981, "out_inject"), (961, "out_inject"), (1000, "out_inject"), (500, "out_plain")):
+        pnp.register_time(None, t, modules=[attn])
+        with torch.no_grad():
+            assert torch.equal(attn(x), torch.from_numpy(g[key])), (t, key)
+    # our own override keeps the module eligible for KD; a foreign override does not
+    assert patch._plain_attention_module(attn)
+    attn.forward = lambda *a, **k: None
+    assert not patch._plain_attention_module(attn)

@@ -30,9 +30,10 @@ def _packed_weights(attn: torch.nn.Module, like: torch.Tensor):
     return cache[1:]
 
 
-def self_attention(attn: torch.nn.Module, x: torch.Tensor) -> torch.Tensor:
-    """softmax(q k^T * scale) v with q,k,v = to_q/to_k/to_v(x), then to_out[0] (utils/pnp_utils.py:47-95)."""
+def self_attention(attn: torch.nn.Module, x: torch.Tensor, shared_qk: bool = False) -> torch.Tensor:
+    """softmax(q k^T * scale) v with q,k,v = to_q/to_k/to_v(x), then to_out[0] (utils/pnp_utils.py:47-95).
+    shared_qk: PnP injection — q and k of sample 0 for every sample (utils/pnp_utils.py:57-68,87-91)."""
     w_qkv, w_o, b_o = _packed_weights(attn, x)
     heads = int(attn.heads)
     scale = float(getattr(attn, "scale", (x.shape[-1] // heads) ** -0.5))
-    return ops.attention(x, w_qkv, w_o, b_o, heads, scale)
+    return ops.attention(x, w_qkv, w_o, b_o, heads, scale, shared_qk=shared_qk)

@@ -129,6 +129,7 @@ struct FaParams {
   // the remaining tiles is cut into `splits` key ranges whose un-normalised results go to part_o / part_ml and
   // are merged by fa_combine_kernel.
   int n_qtiles, n_full, splits;
+  int qk_shared;      // PnP injection (utils/pnp_utils.py:57-68,87-91): q and k of sample 0 for every sample, v per sample
   float* part_o;      // [tile - n_full][splits][BQ][DV_N]  fp32, relative to the part's reference max
   float2* part_ml;    // [tile - n_full][splits][BQ]        (reference max * scale_log2, denominator)
 };
@@ -260,6 +261,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
   const int q0 = (tile % p.n_qtiles) * BQ;
   const int h = (tile / p.n_qtiles) % p.H;
   const int b = tile / (p.n_qtiles * p.H);
+  const int bqk = p.qk_shared ? 0 : b;
   const int nkv_all = (p.L + BKV - 1) / BKV;
   const int j_lo = static_cast<int>(static_cast<long long>(part) * nkv_all / nparts);
   const int nkv = static_cast<int>(static_cast<long long>(part + 1) * nkv_all / nparts) - j_lo;   // >= 1
@@ -297,7 +299,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     // ===================== TMA producer (whole warp converged; one elected lane issues) =====================
     if (elect_one()) {
       mbar_arrive_expect_tx(q_full, C::Q_BYTES);
-      for (int a = 0; a < C::ATOMS; ++a) tma_load_3d(sQ + a * (BQ * 128), &tm_q, q_full, a * 64, q0, b * p.H + h);
+      for (int a = 0; a < C::ATOMS; ++a) tma_load_3d(sQ + a * (BQ * 128), &tm_q, q_full, a * 64, q0, bqk * p.H + h);
     }
     for (int j = 0; j < nkv; ++j) {
       const int s = j % STAGES;
@@ -307,7 +309,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
       const uint32_t sv = sk + C::TILE_BYTES;
       if (elect_one()) {
         mbar_arrive_expect_tx(k_full(s), C::TILE_BYTES);
-        for (int a = 0; a < C::ATOMS; ++a) tma_load_3d(sk + a * C::KV_ATOM, &tm_k, k_full(s), a * 64, (j_lo + j) * BKV, b * p.H + h);
+        for (int a = 0; a < C::ATOMS; ++a) tma_load_3d(sk + a * C::KV_ATOM, &tm_k, k_full(s), a * 64, (j_lo + j) * BKV, bqk * p.H + h);
         mbar_arrive_expect_tx(v_full(s), C::TILE_BYTES);
         for (int a = 0; a < C::ATOMS; ++a) tma_load_3d(sv + a * C::KV_ATOM, &tm_v, v_full(s), a * 64, (j_lo + j) * BKV, b * p.H + h);
       }
@@ -584,7 +586,7 @@ int fa_forced_splits() {
 
 template <int KSTEPS, bool ONES>
 int launch_fa_impl(const void* qkvh, __half* o, void* part_ws, int B, int L, int C, int H, int d, float scale,
-              cudaStream_t stream) {
+              int qk_shared, cudaStream_t stream) {
   using Cf = FaCfg<KSTEPS>;
   using Cg = FaGCfg<KSTEPS>;
   const bool groups = fa_use_groups();
@@ -623,6 +625,7 @@ int launch_fa_impl(const void* qkvh, __half* o, void* part_ws, int B, int L, int
   p.L = L; p.H = H; p.d = d; p.C = C;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.o = o;
+  p.qk_shared = qk_shared;
   p.n_qtiles = (L + BQ - 1) / BQ;
   // Every tile costs the same, so the grid runs in waves of `slots` CTAs and the last, partial wave leaves most of
   // the GPU idle for a whole tile time.  The tiles of that wave are cut into `splits` key ranges instead (chosen to
@@ -665,11 +668,11 @@ int launch_fa_impl(const void* qkvh, __half* o, void* part_ws, int B, int L, int
 
 template <int KSTEPS>
 int launch_fa(const void* qkvh, __half* o, void* part_ws, int B, int L, int C, int H, int d, float scale,
-              cudaStream_t stream) {
+              int qk_shared, cudaStream_t stream) {
 #if !defined(VTM_FA_NO_ONES)   // A/B switch: keep the denominator in the softmax warps
-  if (d % 16 == 8) return launch_fa_impl<KSTEPS, true>(qkvh, o, part_ws, B, L, C, H, d, scale, stream);
+  if (d % 16 == 8) return launch_fa_impl<KSTEPS, true>(qkvh, o, part_ws, B, L, C, H, d, scale, qk_shared, stream);
 #endif
-  return launch_fa_impl<KSTEPS, false>(qkvh, o, part_ws, B, L, C, H, d, scale, stream);
+  return launch_fa_impl<KSTEPS, false>(qkvh, o, part_ws, B, L, C, H, d, scale, qk_shared, stream);
 }
 
 }  // namespace
@@ -685,15 +688,15 @@ extern "C" size_t vtm_attention_workspace_bytes(int32_t B, int32_t L, int32_t C,
   return (static_cast<size_t>(3) * B * heads * L * DP + static_cast<size_t>(B) * L * C) * 2 + vtm::FA_PART_BYTES + 256;
 }
 
-extern "C" int vtm_attention(const void* x_dev, const void* w_qkv_dev, const void* w_o_dev, const void* b_o_dev,
-                             int32_t B, int32_t L, int32_t C, int32_t heads, float scale, void* y_dev,
-                             void* ws_dev, size_t ws_bytes, void* stream_) {
+extern "C" int vtm_attention_ex(const void* x_dev, const void* w_qkv_dev, const void* w_o_dev, const void* b_o_dev,
+                                int32_t B, int32_t L, int32_t C, int32_t heads, float scale, int32_t flags, void* y_dev,
+                                void* ws_dev, size_t ws_bytes, void* stream_) {
   using namespace vtm;
   if (!x_dev || !w_qkv_dev || !w_o_dev || !y_dev || !ws_dev) return VTM_E_NULL;
   if (B <= 0 || L <= 0 || C <= 0 || heads <= 0 || C % heads != 0) return VTM_E_SHAPE;
   const int d = C / heads;
   if (d % 8 != 0 || C % 8 != 0) return VTM_E_SHAPE;
-  if (d > 128) return VTM_E_UNSUPPORTED;
+  if (d > 128 || (flags & ~1) != 0) return VTM_E_UNSUPPORTED;
   if (ws_bytes < vtm_attention_workspace_bytes(B, L, C, heads)) return VTM_E_WS;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int DP = d <= 64 ? 64 : 128;
@@ -705,13 +708,20 @@ extern "C" int vtm_attention(const void* x_dev, const void* w_qkv_dev, const voi
   int rc = launch_qkv_heads(x_dev, w_qkv_dev, qkv, B, L, C, heads, DP, stream);
   if (rc) return rc;
   const int ksteps = (d + 15) / 16;
+  const int shared = flags & 1;
   switch (ksteps) {
-    case 1: case 2: case 3: rc = launch_fa<3>(qkv, o, part_ws, B, L, C, heads, d, scale, stream); break;
-    case 4: rc = launch_fa<4>(qkv, o, part_ws, B, L, C, heads, d, scale, stream); break;
-    case 5: rc = launch_fa<5>(qkv, o, part_ws, B, L, C, heads, d, scale, stream); break;
-    case 6: rc = launch_fa<6>(qkv, o, part_ws, B, L, C, heads, d, scale, stream); break;
-    default: rc = launch_fa<8>(qkv, o, part_ws, B, L, C, heads, d, scale, stream); break;
+    case 1: case 2: case 3: rc = launch_fa<3>(qkv, o, part_ws, B, L, C, heads, d, scale, shared, stream); break;
+    case 4: rc = launch_fa<4>(qkv, o, part_ws, B, L, C, heads, d, scale, shared, stream); break;
+    case 5: rc = launch_fa<5>(qkv, o, part_ws, B, L, C, heads, d, scale, shared, stream); break;
+    case 6: rc = launch_fa<6>(qkv, o, part_ws, B, L, C, heads, d, scale, shared, stream); break;
+    default: rc = launch_fa<8>(qkv, o, part_ws, B, L, C, heads, d, scale, shared, stream); break;
   }
   if (rc) return rc;
   return vtm_linear_f16(o, w_o_dev, b_o_dev, M, C, C, y_dev, C, stream_);
+}
+
+extern "C" int vtm_attention(const void* x_dev, const void* w_qkv_dev, const void* w_o_dev, const void* b_o_dev,
+                             int32_t B, int32_t L, int32_t C, int32_t heads, float scale, void* y_dev,
+                             void* ws_dev, size_t ws_bytes, void* stream_) {
+  return vtm_attention_ex(x_dev, w_qkv_dev, w_o_dev, b_o_dev, B, L, C, heads, scale, 0, y_dev, ws_dev, ws_bytes, stream_);
 }

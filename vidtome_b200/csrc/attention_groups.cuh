@@ -84,6 +84,7 @@ flash_attn_groups_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
   const int q0 = (tile % p.n_qtiles) * BQ;
   const int h = (tile / p.n_qtiles) % p.H;
   const int b = tile / (p.n_qtiles * p.H);
+  const int bqk = p.qk_shared ? 0 : b;
   const int nkv_all = (p.L + BKV - 1) / BKV;
   const int j_lo = static_cast<int>(static_cast<long long>(part) * nkv_all / nparts);
   const int nkv = static_cast<int>(static_cast<long long>(part + 1) * nkv_all / nparts) - j_lo;   // >= 1
@@ -121,7 +122,7 @@ flash_attn_groups_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
       // ===================== TMA producer =====================
       if (elect_one()) {
         mbar_arrive_expect_tx(q_full, C::Q_BYTES);
-        for (int a = 0; a < C::ATOMS; ++a) tma_load_3d(sQ + a * (BQ * 128), &tm_q, q_full, a * 64, q0, b * p.H + h);
+        for (int a = 0; a < C::ATOMS; ++a) tma_load_3d(sQ + a * (BQ * 128), &tm_q, q_full, a * 64, q0, bqk * p.H + h);
       }
       for (int j = 0; j < nkv; ++j) {
         const int s = j % STAGES;
@@ -131,7 +132,7 @@ flash_attn_groups_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
         const uint32_t sv = sk + C::TILE_BYTES;
         if (elect_one()) {
           mbar_arrive_expect_tx(k_full(s), C::TILE_BYTES);
-          for (int a = 0; a < C::ATOMS; ++a) tma_load_3d(sk + a * C::KV_ATOM, &tm_k, k_full(s), a * 64, (j_lo + j) * BKV, b * p.H + h);
+          for (int a = 0; a < C::ATOMS; ++a) tma_load_3d(sk + a * C::KV_ATOM, &tm_k, k_full(s), a * 64, (j_lo + j) * BKV, bqk * p.H + h);
           mbar_arrive_expect_tx(v_full(s), C::TILE_BYTES);
           for (int a = 0; a < C::ATOMS; ++a) tma_load_3d(sv + a * C::KV_ATOM, &tm_v, v_full(s), a * 64, (j_lo + j) * BKV, b * p.H + h);
         }

@@ -336,8 +336,8 @@ def layer_norm(x: torch.Tensor, ln) -> torch.Tensor:
 
 
 def attention(x: torch.Tensor, w_qkv: torch.Tensor, w_o: torch.Tensor, b_o: Optional[torch.Tensor], heads: int,
-              scale: float) -> torch.Tensor:
-    """KD.  x [B, L, C] fp16 -> [B, L, C]."""
+              scale: float, shared_qk: bool = False) -> torch.Tensor:
+    """KD.  x [B, L, C] fp16 -> [B, L, C].  shared_qk: PnP injection — the attention map of sample 0 for every sample."""
     _require(x, torch.float16, "x")
     _require(w_qkv, torch.float16, "w_qkv")
     _require(w_o, torch.float16, "w_o")
@@ -347,8 +347,9 @@ def attention(x: torch.Tensor, w_qkv: torch.Tensor, w_o: torch.Tensor, b_o: Opti
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
     y = torch.empty_like(x)
     with _Timed("KD", 4.0 * B * L * L * Cc + 8.0 * B * L * Cc * Cc, 4.0 * B * L * Cc + 8.0 * Cc * Cc):
-        check(lib.vtm_attention(x.data_ptr(), w_qkv.data_ptr(), w_o.data_ptr(), _ptr(b_o), B, L, Cc, heads,
-                                float(scale), y.data_ptr(), ws.data_ptr(), ws_bytes, _stream()), "vtm_attention")
+        check(lib.vtm_attention_ex(x.data_ptr(), w_qkv.data_ptr(), w_o.data_ptr(), _ptr(b_o), B, L, Cc, heads,
+                                   float(scale), 1 if shared_qk else 0, y.data_ptr(), ws.data_ptr(), ws_bytes, _stream()),
+              "vtm_attention_ex")
     STATS.launches += 3
     return y
 

@@ -203,8 +203,9 @@ def _plain_attention_module(attn: torch.nn.Module) -> bool:
     attention processor (or none), and none of the Attention options that alter the math (group / spatial norm,
     residual connection, output rescale, added KV projections).  Anything else goes through `self.attn1(...)`
     exactly as the reference does (patch.py:157-162), e.g. after `pipe.load_lora_weights` (generate.py:93-94)."""
-    if "forward" in vars(attn):
-        return False
+    override = vars(attn).get("forward")
+    if override is not None and not getattr(override, "_vtm_pnp_forward", False):
+        return False                       # someone else's replaced forward (e.g. the reference's own PnP closure)
     need = ("to_q", "to_k", "to_v", "to_out", "heads")
     if not all(hasattr(attn, n) for n in need):
         return False
@@ -284,7 +285,15 @@ def make_diffusers_tome_block(block_class: Type[torch.nn.Module]) -> Type[torch.
             from . import attention as _attention
             if (plan is not None and _attention.ENABLED and not only_cross and attention_mask is None
                     and not cross_attention_kwargs and _plain_attention_module(self.attn1)):
-                attn_output = _attention.self_attention(self.attn1, norm_hidden_states)  # KD
+                # KD; with PnP control registered (pnp.py) and the timestep inside the injection schedule, the attention
+                # map of the source sample is applied to every sample's values (utils/pnp_utils.py:57-68,87-91)
+                shared = False
+                if getattr(self.attn1, "_vtm_pnp", 0):
+                    from . import pnp as _pnp
+                    shared = _pnp.injection_active(self.attn1)
+                    if shared and norm_hidden_states.shape[0] != self.attn1._vtm_pnp:
+                        raise RuntimeError("PnP injection needs one merged token set per input (batch_size == num_inputs)")
+                attn_output = _attention.self_attention(self.attn1, norm_hidden_states, shared_qk=shared)  # KD
             else:
                 attn_output = self.attn1(
                     norm_hidden_states,
