@@ -264,11 +264,11 @@ flash_attn_groups_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
         }
       }
       if (!ONES) l_run = l_run * alpha + (sum0 + sum1);
-      // O_g rescale: only when a reference max moved, after this group's previous P V has retired.  Having passed
-      // s_full for this tile, the P V two group-tiles back has completed (in-order pipe), so the parity is unambiguous.
+      // O_g rescale: only when a reference max moved.  No wait is needed: the scores of this tile were committed by
+      // QK(j), which the MMA thread issued AFTER this group's previous P V (QK runs G-1 tiles ahead, so QK(j) follows
+      // PV(j - G) in issue order), and a tcgen05.commit covers every MMA issued before it — having passed s_full for
+      // this tile means O_g is at rest.
       if (it > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
-        mbar_wait(o_ready(grp), (it - 1) & 1u);
-        tc_fence_after();
 #pragma unroll
         for (int cb = 0; cb < C::DV_N; cb += 16) {
           uint32_t ro[16];
@@ -285,7 +285,9 @@ flash_attn_groups_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
       if (lane == 0) mbar_arrive(p_full(grp));
     }
     const int n_my = it;
-    if (n_my >= 2) mbar_wait(o_ready(grp), (n_my - 2) & 1u);     // keeps the parity of the next wait unambiguous
+    // o_ready[g] is waited on exactly once: by now it has completed n_my - 1 or n_my times (the last P V needed this
+    // thread's p_full arrival; all earlier ones are covered by the s_full argument above), so the parity of completion
+    // n_my - 1 is unambiguous.
     if (n_my >= 1) mbar_wait(o_ready(grp), (n_my - 1) & 1u);
     tc_fence_after();
     // ---- exchange (reference max in log2 units, denominator) and merge the groups' accumulators
