@@ -11,8 +11,9 @@
  *     passed as void* (torch.cuda.current_stream().cuda_stream);
  *   - token matrices are fp16, row-major, rows of C contiguous halfs, C % 8 == 0, 16-byte aligned;
  *   - index maps are int32; "batch stride 0" means one map shared by all samples (align_batch);
- *   - the functions never allocate, never synchronise the stream, keep no mutable global state
- *     (re-entrant across streams and devices), and never throw;
+ *   - the functions never allocate, never synchronise the stream, and never throw; the only process-wide
+ *     state is a handful of write-once memoised lookups (driver entry point, SM count, per-kernel shared-memory opt-in
+ *     and occupancy), immutable after first use, so calls are re-entrant across streams and devices;
  *   - return value: 0 = ok, <0 = bad argument (VTM_E_*), >0 = a cudaError_t / CUresult reported by
  *     the launch.  There is no CPU fallback: without a CUDA device the compute entry points return
  *     the CUDA error of the failed launch.
@@ -115,6 +116,11 @@ int vtm_normalize_split_ln(const void* x_dev, int64_t x_batch_stride, const int3
  */
 int vtm_sim_argmax(const void* a_dev, const void* b_dev, int32_t B, int32_t Ns, int32_t Nd,
                    int32_t C, int32_t align_batch, uint64_t* keys_out_dev, void* stream);
+
+/* KA built on CTA pairs (tcgen05 cta_group::2: 256-row src blocks, each CTA loads half of every dst tile).  Same
+ * results bit for bit; measured and not faster on B200, kept for A/B measurements and tests. */
+int vtm_sim_argmax_pair(const void* a_dev, const void* b_dev, int32_t B, int32_t Ns, int32_t Nd,
+                        int32_t C, int32_t align_batch, uint64_t* keys_out_dev, void* stream);
 
 /* Debug/verification twin of KA on CUDA cores (one thread per src row, sequential fp32 FMA over K
  * in index order).  Same outputs; used by tests to cross-check KA at sizes the CPU oracle cannot

@@ -111,11 +111,9 @@ def test_sim_argmax_bit_exact_on_exact_inputs(B, Ns, Nd, C, align, ka_variant):
 
 @pytest.fixture(params=["cta", "cta_pair"])
 def ka_variant(request, monkeypatch):
-    """KA's default kernel and its CTA-pair (cta_group::2) build, selected per call by VTM_KA_2CTA."""
-    if request.param == "cta_pair":
-        monkeypatch.setenv("VTM_KA_2CTA", "1")
-    else:
-        monkeypatch.delenv("VTM_KA_2CTA", raising=False)
+    """KA's default kernel and its CTA-pair (cta_group::2) build (vtm_sim_argmax / vtm_sim_argmax_pair)."""
+    from vidtome_b200 import ops
+    monkeypatch.setattr(ops, "KA_VARIANT", "pair" if request.param == "cta_pair" else "cta")
     return request.param
 
 
@@ -167,9 +165,9 @@ def test_sim_argmax_cta_pair_equals_default(monkeypatch):
                                   (1, 77, 33, 64, False)]:
         a = torch.randn((B, Ns, C), generator=g, device="cuda").half()
         b = torch.randn((B, Nd, C), generator=g, device="cuda").half()
-        monkeypatch.delenv("VTM_KA_2CTA", raising=False)
+        monkeypatch.setattr(ops, "KA_VARIANT", "cta")
         k1 = ops.sim_argmax(a, b, align)
-        monkeypatch.setenv("VTM_KA_2CTA", "1")
+        monkeypatch.setattr(ops, "KA_VARIANT", "pair")
         k2 = ops.sim_argmax(a, b, align)
         assert torch.equal(k1, k2)
 

@@ -1,4 +1,4 @@
-"""A/B of the KA variants selected by the VTM_KA_2CTA environment toggle (read per call by the library):
+"""A/B of the KA variants selected by ops.KA_VARIANT (vtm_sim_argmax vs vtm_sim_argmax_pair):
 bit-exact check of each variant against the SIMT twin, then interleaved timing at the benchmark shapes."""
 import json
 import os
@@ -12,9 +12,9 @@ from vidtome_b200 import ops  # noqa: E402
 
 def set_variant(two_cta: bool):
     if two_cta:
-        os.environ["VTM_KA_2CTA"] = "1"
+        ops.KA_VARIANT = "pair"
     else:
-        os.environ.pop("VTM_KA_2CTA", None)
+        ops.KA_VARIANT = "cta"
 
 
 def check(B, Ns, Nd, C, align):

@@ -11,9 +11,9 @@ a = torch.randn(2, 49152, 320, device="cuda").half()
 b = torch.randn(2, 16384, 320, device="cuda").half()
 for v in (None, "1"):
     if v:
-        os.environ["VTM_KA_2CTA"] = v
+        ops.KA_VARIANT = "pair"
     else:
-        os.environ.pop("VTM_KA_2CTA", None)
+        ops.KA_VARIANT = "cta"
     for _ in range(2):
         ops.sim_argmax(a, b, False)
     torch.cuda.synchronize()

@@ -26,9 +26,8 @@ for (B, L, C, H) in [(1, 333, 320, 8), (2, 2561, 640, 8)]:
 info = {"size": (16, 16), "args": dict(max_downsample=2, batch_size=2, align_batch=False, merge_global=False,
                                         global_merge_ratio=0.8, local_merge_ratio=0.9, global_rand=0.5, target_stride=4)}
 x = torch.randn((2 * 8, 256, 320), generator=g, device="cuda").half()
-for env in (None, "1"):
-    if env:
-        os.environ["VTM_KA_2CTA"] = env
+for variant in ("cta", "pair"):
+    ops.KA_VARIANT = variant
     mod = SimpleNamespace(generator=torch.Generator(device="cuda").manual_seed(1), global_tokens=None)
     plan = patch.build_merge_plan(mod, x, info)
     out = plan.unmerge_add(plan.merged_tokens, x)

@@ -605,18 +605,24 @@ int launch_fa_impl(const void* qkvh, __half* o, void* part_ws, int B, int L, int
   int sms = 0, per_sm = 1;
   rc = gemm::device_sms(&sms);
   if (rc) return rc;
-  // one-time per instantiation: shared-memory opt-in and occupancy (immutable afterwards)
-  static int attr_rc = -1, occ = 0;
-  if (attr_rc != 0) {
-    attr_rc = cuda_rc(cudaFuncSetAttribute(flash_attn_kernel<KSTEPS, ONES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           static_cast<int>(Cf::SMEM_BYTES)));
-    if (attr_rc) return attr_rc;
-    attr_rc = cuda_rc(cudaFuncSetAttribute(flash_attn_groups_kernel<KSTEPS, ONES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           static_cast<int>(Cg::SMEM_BYTES)));
-    if (attr_rc) return attr_rc;
-    attr_rc = cuda_rc(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, flash_attn_kernel<KSTEPS, ONES>, FA_THREADS,
-                                                                    Cf::SMEM_BYTES));
-    if (attr_rc) return attr_rc;
+  // once per instantiation and device: shared-memory opt-in and occupancy (immutable afterwards)
+  static int occ_tab[64];
+  int dev = 0;
+  rc = cuda_rc(cudaGetDevice(&dev));
+  if (rc) return rc;
+  int occ = (dev >= 0 && dev < 64) ? occ_tab[dev] : 0;
+  if (occ == 0) {
+    rc = cuda_rc(cudaFuncSetAttribute(flash_attn_kernel<KSTEPS, ONES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(Cf::SMEM_BYTES)));
+    if (rc) return rc;
+    rc = cuda_rc(cudaFuncSetAttribute(flash_attn_groups_kernel<KSTEPS, ONES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(Cg::SMEM_BYTES)));
+    if (rc) return rc;
+    rc = cuda_rc(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, flash_attn_kernel<KSTEPS, ONES>, FA_THREADS,
+                                                               Cf::SMEM_BYTES));
+    if (rc) return rc;
+    if (occ < 1) occ = 1;
+    if (dev >= 0 && dev < 64) occ_tab[dev] = occ;
   }
   per_sm = groups ? 1 : (occ > 0 ? occ : 1);
   const int slots = sms * per_sm;

@@ -97,13 +97,38 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuin
                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 inline PFN_tmapEncodeTiled get_tmap_encode() {
-  // Resolved on every call (cheap, and keeps the library free of mutable globals).
+  // Resolved once per process (the answer cannot change); immutable afterwards, so the entry points stay re-entrant.
+  static const PFN_tmapEncodeTiled cached = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return static_cast<PFN_tmapEncodeTiled>(nullptr);
+    return reinterpret_cast<PFN_tmapEncodeTiled>(fn);
+  }();
+  if (cached) return cached;
+  // not resolvable at first use (no driver yet): try again so that a later call can succeed
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult q;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
       q != cudaDriverEntryPointSuccess)
     return nullptr;
   return reinterpret_cast<PFN_tmapEncodeTiled>(fn);
+}
+
+// Number of SMs of the current device; looked up once per device ordinal (immutable afterwards).
+inline int cached_sm_count(int* sms) {
+  static int table[64];          // 0 = unknown; written once per slot with the same value by any thread
+  int dev = 0;
+  int rc = cuda_rc(cudaGetDevice(&dev));
+  if (rc) return rc;
+  if (dev >= 0 && dev < 64 && table[dev] > 0) { *sms = table[dev]; return VTM_OK; }
+  int n = 0;
+  rc = cuda_rc(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  if (rc) return rc;
+  if (dev >= 0 && dev < 64) table[dev] = n;
+  *sms = n;
+  return VTM_OK;
 }
 
 // fp16 tensor [d2][d1][d0] (d0 contiguous), row pitch ld1 elements, slab pitch ld2 elements; box

@@ -277,20 +277,23 @@ inline int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Work& wk, 
                   cudaStream_t stream) {
   using C = Cfg<BN>;
   const size_t smem = C::SMEM_BYTES + static_cast<size_t>(EPI_WARPS) * Epi::SCRATCH_PER_WARP;
-  int rc = cuda_rc(cudaFuncSetAttribute(gemm_kernel<BN, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(smem)));
+  // shared-memory opt-in: once per instantiation and device (a per-function, per-device attribute; immutable afterwards)
+  static bool opted[64];
+  int dev = 0;
+  int rc = cuda_rc(cudaGetDevice(&dev));
   if (rc) return rc;
+  if (dev < 0 || dev >= 64 || !opted[dev]) {
+    rc = cuda_rc(cudaFuncSetAttribute(gemm_kernel<BN, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+    if (rc) return rc;
+    if (dev >= 0 && dev < 64) opted[dev] = true;
+  }
   const int grid = wk.total < sms ? wk.total : sms;
   gemm_kernel<BN, Epi><<<grid, THREADS, smem, stream>>>(ta, tb, wk, epi);
   return launch_rc();
 }
 
-inline int device_sms(int* sms) {
-  int dev = 0;
-  int rc = cuda_rc(cudaGetDevice(&dev));
-  if (rc) return rc;
-  return cuda_rc(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev));
-}
+inline int device_sms(int* sms) { return cached_sm_count(sms); }
 
 }  // namespace gemm
 }  // namespace vtm

@@ -253,12 +253,7 @@ gather_rows_kernel(const __half* __restrict__ x, long long x_bs, const int* __re
   }
 }
 
-int sm_count(int* sms) {
-  int dev = 0;
-  int rc = cuda_rc(cudaGetDevice(&dev));
-  if (rc) return rc;
-  return cuda_rc(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev));
-}
+int sm_count(int* sms) { return cached_sm_count(sms); }
 
 // Grid of a grid-stride row kernel: never more CTAs than are resident at once (sms x the kernel's occupancy), so
 // that all warps run the same number of iterations (+-1) instead of a short last wave.

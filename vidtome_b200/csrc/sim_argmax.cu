@@ -147,9 +147,10 @@ int check_args(const void* a, const void* b, int B, int Ns, int Nd, int C, const
 }  // namespace
 }  // namespace vtm
 
-extern "C" int vtm_sim_argmax(const void* a_dev, const void* b_dev, int32_t B, int32_t Ns, int32_t Nd,
-                              int32_t C, int32_t align_batch, uint64_t* keys_out_dev, void* stream_) {
-  using namespace vtm;
+namespace vtm {
+namespace {
+int sim_argmax_impl(const void* a_dev, const void* b_dev, int32_t B, int32_t Ns, int32_t Nd, int32_t C,
+                    int32_t align_batch, uint64_t* keys_out_dev, void* stream_, bool use_pair) {
   int rc = check_args(a_dev, b_dev, B, Ns, Nd, C, keys_out_dev);
   if (rc) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -176,7 +177,7 @@ extern "C" int vtm_sim_argmax(const void* a_dev, const void* b_dev, int32_t B, i
   epi.keys = reinterpret_cast<unsigned long long*>(keys_out_dev);
   epi.Ns = Ns; epi.Nd = Nd; epi.align_batch = align_batch ? 1 : 0;
   epi.best = 0.f; epi.best_idx = 0;
-  if (getenv("VTM_KA_2CTA") != nullptr) {
+  if (use_pair) {
     // CTA-pair variant: 256-row src blocks per pair, B tensor map with 128-row boxes (each CTA loads half a tile)
     CUtensorMap tb2;
     rc = make_tmap_3d_f16(&tb2, b_dev, C, Nd, B, C, static_cast<uint64_t>(Nd) * C, gemm::BK, 128);
@@ -195,6 +196,18 @@ extern "C" int vtm_sim_argmax(const void* a_dev, const void* b_dev, int32_t B, i
     return gemm::launch_2cta<ArgmaxEpi>(ta, tb2, wk2, epi, sms, stream);
   }
   return gemm::launch<BN, ArgmaxEpi>(ta, tb, wk, epi, sms, stream);
+}
+}  // namespace
+}  // namespace vtm
+
+extern "C" int vtm_sim_argmax(const void* a_dev, const void* b_dev, int32_t B, int32_t Ns, int32_t Nd,
+                              int32_t C, int32_t align_batch, uint64_t* keys_out_dev, void* stream_) {
+  return vtm::sim_argmax_impl(a_dev, b_dev, B, Ns, Nd, C, align_batch, keys_out_dev, stream_, false);
+}
+
+extern "C" int vtm_sim_argmax_pair(const void* a_dev, const void* b_dev, int32_t B, int32_t Ns, int32_t Nd,
+                                   int32_t C, int32_t align_batch, uint64_t* keys_out_dev, void* stream_) {
+  return vtm::sim_argmax_impl(a_dev, b_dev, B, Ns, Nd, C, align_batch, keys_out_dev, stream_, true);
 }
 
 extern "C" int vtm_sim_argmax_simt(const void* a_dev, const void* b_dev, int32_t B, int32_t Ns,

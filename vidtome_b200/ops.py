@@ -111,6 +111,9 @@ def normalize_split(x: torch.Tensor, rowmap: Optional[torch.Tensor], split: VtmS
     return a, b
 
 
+KA_VARIANT = "cta"     # "cta" (default) | "pair" (cta_group::2 build, A/B measurements and tests)
+
+
 def sim_argmax(a: torch.Tensor, b: torch.Tensor, align_batch: bool, simt: bool = False) -> torch.Tensor:
     """KA.  Returns the packed keys [B'|Ns] as an int64 tensor (bit pattern of the uint64 keys)."""
     _require(a, torch.float16, "a")
@@ -118,7 +121,8 @@ def sim_argmax(a: torch.Tensor, b: torch.Tensor, align_batch: bool, simt: bool =
     B, Ns, Cc = a.shape
     Nd = b.shape[1]
     keys = torch.empty((1 if align_batch else B, Ns), dtype=torch.int64, device=a.device)
-    fn = _lib.load().vtm_sim_argmax_simt if simt else _lib.load().vtm_sim_argmax
+    lib = _lib.load()
+    fn = lib.vtm_sim_argmax_simt if simt else (lib.vtm_sim_argmax_pair if KA_VARIANT == "pair" else lib.vtm_sim_argmax)
     with _Timed("KA", 2.0 * B * Ns * Nd * Cc, 2.0 * B * (Ns + Nd) * Cc + 8.0 * keys.shape[0] * Ns):
         check(fn(a.data_ptr(), b.data_ptr(), B, Ns, Nd, Cc, int(bool(align_batch)), keys.data_ptr(), _stream()),
               "vtm_sim_argmax")
