@@ -68,7 +68,7 @@ def child():
 def main():
     vdir = os.path.join(ROOT, "build", "variants")
     names = ["default"] + sorted(n for n in os.listdir(vdir) if os.path.exists(os.path.join(vdir, n, "libvidtome_b200.so"))) if os.path.isdir(vdir) else ["default"]
-    runs = [(n, {}) for n in names] + [(n + "_2cta_per_sm", {"VTM_FA_GROUPS": "0"}) for n in names if n in ("default", "poly00")]
+    runs = [(n, {}) for n in names] + [(n + "_2cta_per_sm", {"VTM_FA_GROUPS": "0"}) for n in names]
     for n, extra in runs:
         env = dict(os.environ, VTM_VARIANT=n, **extra)
         base = n.replace("_2cta_per_sm", "")

@@ -117,6 +117,12 @@ int launch_qkv_heads(const void* x, const void* w_qkv, __half* qkvh, int B, int 
   return gemm::launch<128, HeadSplitEpi>(ta, tb, wk, epi, sms, stream);
 }
 
+#ifndef VTM_FA2_STAGGER_NS
+#define VTM_FA2_STAGGER_NS 300
+#endif
+// per-SM start counter of the two-CTAs-per-SM kernel (a scheduling hint only: its parity decides which CTA staggers)
+__device__ unsigned int vtm_fa_sm_slot[256];
+
 constexpr int BQ = 128;    // query rows per CTA (UMMA M)
 constexpr int FA_THREADS = 192;
 constexpr float RESCALE_LOG2 = 8.f;   // move the reference max only when exceeded by 2^8
@@ -372,6 +378,22 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     const float c = p.scale_log2;
     float m_ref = -INFINITY;   // reference max (raw score units) used by the exponentials
     float l_run = 0.f;         // running denominator (same reference)
+#if VTM_FA2_STAGGER_NS > 0
+    // Two co-resident CTAs run the same instruction stream on equally long tiles and tend to stay in lock-step (both in
+    // their MUFU phase, then both out of it).  Every second CTA that starts on an SM delays its softmax warps once by
+    // about a third of a tile time so that the phases interleave.
+    {
+      uint32_t smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      uint32_t slot = 0;
+      if (lane == 0 && quad == 0) slot = atomicAdd(&vtm_fa_sm_slot[smid & 255u], 1u);
+      // one draw per CTA, broadcast to the four softmax warps through the (already initialised) tmem pointer slot + 4
+      if (lane == 0 && quad == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(tmem_ptr_addr + 4), "r"(slot) : "memory");
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(slot) : "r"(tmem_ptr_addr + 4));
+      if (slot & 1u) __nanosleep(VTM_FA2_STAGGER_NS);
+    }
+#endif
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(s_full(j & 1), (j >> 1) & 1u);
       tc_fence_after();

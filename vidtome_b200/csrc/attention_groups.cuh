@@ -16,6 +16,10 @@
 // TMEM: S_g at [g BKV, (g+1) BKV) (P_g overwrites it as fp16), O_g at [G BKV + g DV_N, ...).
 #pragma once
 
+#ifndef VTM_FA_STAGGER_NS
+#define VTM_FA_STAGGER_NS 150
+#endif
+
 namespace vtm {
 namespace {
 
@@ -205,6 +209,13 @@ flash_attn_groups_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
     float m_ref = -INFINITY;
     float l_run = 0.f;
     int it = 0;
+#if VTM_FA_STAGGER_NS > 0
+    // The groups run identical instruction streams on tiles that become ready together, so left alone they stay in
+    // lock-step: all in their MUFU phase at once (sharing the XU pipe), then all in their load / convert / store phase
+    // (XU idle).  A one-off offset of a fraction of a tile time per group makes the phases interleave; nothing
+    // re-synchronises them afterwards (ncu r02: XU pipe 62 % busy in lock-step).
+    if (grp > 0) __nanosleep(VTM_FA_STAGGER_NS * grp);
+#endif
     for (int j = grp; j < nkv; j += G, ++it) {
       mbar_wait(s_full(grp), it & 1u);
       tc_fence_after();
