@@ -253,6 +253,20 @@ int vtm_linear_f16(const void* a_dev, const void* w_dev, const void* bias_dev, i
                    int32_t K, void* d_dev, int64_t ldd, void* stream);
 
 /*
+ * Cross-attention of the patched block.  Replaces `self.attn2(norm2(h), encoder_hidden_states=ctx) + h`
+ * (vidtome/patch.py:171-185; diffusers Attention with K/V taken from the text context):
+ *   q = x Wq^T, [k | v] = ctx [Wk; Wv]^T (no bias), per-head softmax(q k^T * scale) v, y = o Wo^T + bo (+ resid).
+ *   x_dev [B, Lq, C] fp16 (norm2 output); ctx_dev [B, Lk, Cctx] fp16; w_q_dev [C, C]; w_kv_dev [2C, Cctx] (rows Wk | Wv);
+ *   w_o_dev [C, C]; b_o_dev [C] or NULL; resid_dev [B, Lq, C] or NULL; y_dev [B, Lq, C].
+ *   B counts (sample x frame) items: every item attends to its own Lk context rows.  head_dim % 8 == 0, <= 128.
+ */
+size_t vtm_cross_attention_workspace_bytes(int32_t B, int32_t Lq, int32_t Lk, int32_t C, int32_t heads);
+int vtm_cross_attention(const void* x_dev, const void* ctx_dev, const void* w_q_dev, const void* w_kv_dev,
+                        const void* w_o_dev, const void* b_o_dev, const void* resid_dev, int32_t B, int32_t Lq,
+                        int32_t Lk, int32_t C, int32_t Cctx, int32_t heads, float scale, void* y_dev, void* ws_dev,
+                        size_t ws_bytes, void* stream);
+
+/*
  * Feed-forward of the patched block (vidtome/patch.py:187-199 calls `self.ff(norm3(h))` and adds the residual; the
  * module is diffusers' FeedForward = GEGLU(dim -> 4 dim) -> Dropout -> Linear(4 dim -> dim)) on tcgen05:
  *

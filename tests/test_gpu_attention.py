@@ -148,3 +148,54 @@ def test_pnp_block_path_uses_kd_with_injection():
             A.ENABLED = True
     err = (outs[0] - outs[1]).abs().max().item()
     assert err <= 2e-3 * outs[1].abs().max().item() + 1e-3
+
+
+@pytest.mark.parametrize("B,Lq,Lk,C,Cctx,heads", [(6, 500, 77, 320, 768, 8), (4, 1024, 77, 640, 768, 8), (3, 130, 7, 128, 32, 2),
+                                                    (2, 300, 77, 320, 1024, 5)])
+def test_cross_attention_matches_fp32_reference(B, Lq, Lk, C, Cctx, heads):
+    """f3: attn2 of the block (77 text tokens as keys/values, vidtome/patch.py:171-185) through vtm_cross_attention,
+    with the residual fused, against fp32 torch."""
+    from vidtome_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(Lq)
+    x = torch.randn((B, Lq, C), generator=g, device="cuda").half()
+    ctx = torch.randn((B, Lk, Cctx), generator=g, device="cuda").half()
+    wq = (torch.randn((C, C), generator=g, device="cuda") / C ** 0.5).half()
+    wk = (torch.randn((C, Cctx), generator=g, device="cuda") / Cctx ** 0.5).half()
+    wv = (torch.randn((C, Cctx), generator=g, device="cuda") / Cctx ** 0.5).half()
+    wo = (torch.randn((C, C), generator=g, device="cuda") / C ** 0.5).half()
+    bo = (0.1 * torch.randn((C,), generator=g, device="cuda")).half()
+    resid = torch.randn((B, Lq, C), generator=g, device="cuda").half()
+    d = C // heads
+    y = ops.cross_attention(x, ctx, wq, torch.cat([wk, wv], 0).contiguous(), wo, bo, heads, d ** -0.5, resid=resid)
+    q = (x.float() @ wq.float().t()).view(B, Lq, heads, d).transpose(1, 2)
+    k = (ctx.float() @ wk.float().t()).view(B, Lk, heads, d).transpose(1, 2)
+    v = (ctx.float() @ wv.float().t()).view(B, Lk, heads, d).transpose(1, 2)
+    o = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, Lq, C)
+    ref = o @ wo.float().t() + bo.float() + resid.float()
+    err = (y.float() - ref).abs().max().item()
+    assert err <= 1e-3 * ref.abs().max().item() + 2e-3
+    y2 = ops.cross_attention(x, ctx, wq, torch.cat([wk, wv], 0).contiguous(), wo, bo, heads, d ** -0.5)
+    assert (y2.float() - (ref - resid.float())).abs().max().item() <= 1e-3 * ref.abs().max().item() + 2e-3
+
+
+def test_full_block_fast_paths_match_module_paths():
+    """A full patched block (self-attention section + cross-attention + GEGLU feed-forward) with every fast path on
+    equals the same block with attn2 / ff running through their torch modules (FUSE_* switches off)."""
+    import vidtome_b200
+    from vidtome_b200 import patch
+    from vidtome_b200.skeleton import make_skeleton
+    outs = []
+    for fast in (True, False):
+        patch.FUSE_CROSS_ATTENTION = patch.FUSE_FEED_FORWARD = fast
+        try:
+            net = make_skeleton("tiny", device="cuda", hot_path_only=False, seed=11)
+            vidtome_b200.apply_patch(net, batch_size=2, local_merge_ratio=1.0)
+            torch.manual_seed(2); torch.cuda.manual_seed(2)
+            lat = torch.randn(2 * 4, 4, 16, 16, device="cuda", dtype=torch.float16)
+            ctx = torch.randn(2 * 4, 77, 768, device="cuda", dtype=torch.float16)
+            with torch.no_grad():
+                outs.append(net(lat, 0, encoder_hidden_states=ctx).sample.float())
+        finally:
+            patch.FUSE_CROSS_ATTENTION = patch.FUSE_FEED_FORWARD = True
+    err = (outs[0] - outs[1]).abs().max().item()
+    assert err <= 3e-3 * outs[1].abs().max().item()

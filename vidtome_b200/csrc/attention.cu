@@ -27,6 +27,8 @@
 
 extern "C" int vtm_linear_f16(const void*, const void*, const void*, int32_t, int32_t, int32_t, void*, int64_t,
                               void*);
+extern "C" int vtm_linear_residual_f16(const void*, const void*, const void*, const void*, int64_t, int32_t, int32_t,
+                                       int32_t, void*, int64_t, void*);
 
 namespace vtm {
 namespace {
@@ -42,6 +44,7 @@ struct HeadSplitEpi {
   static constexpr uint32_t SCRATCH_PER_WARP = gemm::STAGE_STORE_BYTES;
   __half* qkvh;
   int M, C, H, d, L, DP, nb; // M = nb*L rows, C = H*d
+  int which0, n_proj;        // this GEMM produces projections which0 .. which0 + n_proj - 1 of (q, k, v); N = n_proj * C
   long long which_stride;    // B*H*L*DP
   int row0;                  // first of the warp's 32 rows
   uint32_t scratch;
@@ -68,7 +71,7 @@ struct HeadSplitEpi {
       for (int e = 0; e < 32; ++e) pk[e] = pack_f16x2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
       // this lane's 8 columns in the store phase: the same for all of its rows
       const int n = col0 + cb + (threadIdx.x & 7) * 8;       // groups of 8 columns never straddle a head (d % 8 == 0)
-      const bool n_ok = n < 3 * C;
+      const bool n_ok = n < n_proj * C;
       const int which = n / C, c = n - which * C;
       const int head = c / d, e0 = c - head * d;
       const bool last_group = e0 + 8 == d;                   // then this lane also zeroes the head's padding columns
@@ -85,7 +88,7 @@ struct HeadSplitEpi {
             // padding columns: zeros — except column d of V, which holds 1.0 so that the P V MMA also produces
             // the softmax denominator (flash_attn_kernel, ONES)
             const uint4 z = make_uint4(0, 0, 0, 0);
-            *reinterpret_cast<uint4*>(dst + 8) = which == 2 ? make_uint4(0x00003C00u, 0, 0, 0) : z;
+            *reinterpret_cast<uint4*>(dst + 8) = which + which0 == 2 ? make_uint4(0x00003C00u, 0, 0, 0) : z;
             for (int pe = d + 8; pe < DP; pe += 8) *reinterpret_cast<uint4*>(dst + 8 + (pe - d)) = z;
           }
         }
@@ -98,23 +101,31 @@ struct HeadSplitEpi {
   __device__ __forceinline__ void end(int, int, int) {}
 };
 
-int launch_qkv_heads(const void* x, const void* w_qkv, __half* qkvh, int B, int L, int C, int H, int DP,
-                     cudaStream_t stream) {
+// x [nb * L, K] -> projections which0 .. which0 + n_proj - 1 of (q, k, v), head-major padded, at `out`
+// ([n_proj][nb][H][L][DP]); w [n_proj * C, K].
+int launch_head_proj(const void* x, const void* w, __half* out, int nb, int L, int K, int C, int H, int DP, int which0,
+                     int n_proj, cudaStream_t stream) {
   int sms = 0;
   int rc = gemm::device_sms(&sms);
   if (rc) return rc;
-  const int M = B * L, N = 3 * C;
+  const int M = nb * L, N = n_proj * C;
   HeadSplitEpi epi;
-  epi.qkvh = qkvh; epi.M = M; epi.C = C; epi.H = H; epi.d = C / H; epi.L = L; epi.DP = DP;
-  epi.which_stride = static_cast<long long>(B) * H * L * DP; epi.row0 = 0; epi.scratch = 0; epi.b0 = 0; epi.l0 = 0; epi.nb = B;
+  epi.qkvh = out; epi.M = M; epi.C = C; epi.H = H; epi.d = C / H; epi.L = L; epi.DP = DP;
+  epi.which0 = which0; epi.n_proj = n_proj;
+  epi.which_stride = static_cast<long long>(nb) * H * L * DP; epi.row0 = 0; epi.scratch = 0; epi.b0 = 0; epi.l0 = 0; epi.nb = nb;
   CUtensorMap ta, tb;
-  rc = make_tmap_3d_f16(&ta, x, C, M, 1, C, static_cast<uint64_t>(M) * C, gemm::BK, gemm::BM);
+  rc = make_tmap_3d_f16(&ta, x, K, M, 1, K, static_cast<uint64_t>(M) * K, gemm::BK, gemm::BM);
   if (rc) return rc;
-  rc = make_tmap_3d_f16(&tb, w_qkv, C, N, 1, C, static_cast<uint64_t>(N) * C, gemm::BK, 128);
+  rc = make_tmap_3d_f16(&tb, w, K, N, 1, K, static_cast<uint64_t>(N) * K, gemm::BK, 128);
   if (rc) return rc;
   gemm::Work wk;
-  wk.plan(M, N, C, 1, 128, sms, 16, 1);
+  wk.plan(M, N, K, 1, 128, sms, 16, 1);
   return gemm::launch<128, HeadSplitEpi>(ta, tb, wk, epi, sms, stream);
+}
+
+int launch_qkv_heads(const void* x, const void* w_qkv, __half* qkvh, int B, int L, int C, int H, int DP,
+                     cudaStream_t stream) {
+  return launch_head_proj(x, w_qkv, qkvh, B, L, C, C, H, DP, 0, 3, stream);
 }
 
 #ifndef VTM_FA2_STAGGER_NS
@@ -128,7 +139,8 @@ constexpr int FA_THREADS = 192;
 constexpr float RESCALE_LOG2 = 8.f;   // move the reference max only when exceeded by 2^8
 
 struct FaParams {
-  int L, H, d, C;
+  int L, H, d, C;     // L = number of keys per (sample, head)
+  int Lq;             // number of queries per sample (== L for self-attention)
   float scale_log2;   // softmax scale * log2(e)
   __half* o;          // [B*L, C]
   // Work decomposition (see launch_fa): units [0, n_full) are whole (query tile, head, sample) problems; each of
@@ -489,13 +501,13 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     if (nparts == 1) {
       // ---- epilogue: O / l -> fp16 -> o[b, row, h*d : h*d + d]
       const float inv = 1.f / l_run;
-      __half* orow = p.o + (static_cast<size_t>(b) * p.L + row) * p.C + h * p.d;
+      __half* orow = p.o + (static_cast<size_t>(b) * p.Lq + row) * p.C + h * p.d;
 #pragma unroll
       for (int cb = 0; cb < C::DV_N; cb += 16) {
         uint32_t r[16];
         tmem_ld_32x32b_x16(tmem_o + lane_field + cb, r);
         tmem_ld_wait();
-        if (row < p.L) {
+        if (row < p.Lq) {
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             if (cb + g * 8 < p.d) {  // d % 8 == 0
@@ -548,7 +560,7 @@ __global__ void fa_combine_kernel(const FaParams p, int dv_n, int n_split_tiles)
   const int st = static_cast<int>(t / (static_cast<long long>(groups) * BQ));
   const int tile = p.n_full + st;
   const int row = (tile % p.n_qtiles) * BQ + r;
-  if (row >= p.L) return;
+  if (row >= p.Lq) return;
   const int h = (tile / p.n_qtiles) % p.H;
   const int b = tile / (p.n_qtiles * p.H);
   const size_t prow0 = static_cast<size_t>(st) * p.splits * BQ + r;
@@ -575,7 +587,7 @@ __global__ void fa_combine_kernel(const FaParams p, int dv_n, int n_split_tiles)
     const __half2 hh = __floats2half2_rn(acc[2 * e] * inv, acc[2 * e + 1] * inv);
     pv[e] = *reinterpret_cast<const uint32_t*>(&hh);
   }
-  *reinterpret_cast<uint4*>(p.o + (static_cast<size_t>(b) * p.L + row) * p.C + h * p.d + g * 8) = v;
+  *reinterpret_cast<uint4*>(p.o + (static_cast<size_t>(b) * p.Lq + row) * p.C + h * p.d + g * 8) = v;
 }
 
 }  // namespace
@@ -589,12 +601,13 @@ constexpr int FA_MAX_SPLIT_UNITS = 320;
 constexpr int FA_MAX_SPLITS = 8;
 constexpr size_t FA_PART_BYTES = static_cast<size_t>(FA_MAX_SPLIT_UNITS) * BQ * (128 * sizeof(float) + sizeof(float2));
 
-// Which flash kernel: the grouped one (attention_groups.cuh: one CTA per SM, G softmax groups) unless VTM_FA_GROUPS=0
-// asks for the two-CTAs-per-SM kernel above (A/B measurements).  Read once; immutable afterwards.
+// Which flash kernel: the two-CTAs-per-SM kernel above by default; VTM_FA_GROUPS=1 selects the grouped one
+// (attention_groups.cuh: one CTA per SM, G softmax groups), which measured 4-7 % slower at the SD shapes
+// (profiles/r02_attention_kernel_study.md).  Read once per process; immutable afterwards.
 bool fa_use_groups() {
   static const int v = [] {
     const char* e = getenv("VTM_FA_GROUPS");
-    return (e && e[0] == '0') ? 0 : 1;
+    return (e && e[0] == '1') ? 1 : 0;
   }();
   return v != 0;
 }
@@ -607,8 +620,8 @@ int fa_forced_splits() {
 }
 
 template <int KSTEPS, bool ONES>
-int launch_fa_impl(const void* qkvh, __half* o, void* part_ws, int B, int L, int C, int H, int d, float scale,
-              int qk_shared, cudaStream_t stream) {
+int launch_fa_impl(const void* qh, const void* kh, const void* vh, __half* o, void* part_ws, int B, int Lq, int L, int C,
+                   int H, int d, float scale, int qk_shared, cudaStream_t stream) {
   using Cf = FaCfg<KSTEPS>;
   using Cg = FaGCfg<KSTEPS>;
   const bool groups = fa_use_groups();
@@ -616,13 +629,11 @@ int launch_fa_impl(const void* qkvh, __half* o, void* part_ws, int B, int L, int
   CUtensorMap tq, tk, tv;
   const int DP = Cf::ATOMS * 64;                       // padded head_dim of the head-major q/k/v buffers
   const uint64_t BH = static_cast<uint64_t>(B) * H;
-  const __half* base = static_cast<const __half*>(qkvh);
-  const uint64_t which_stride = BH * L * DP;
-  int rc = make_tmap_3d_f16(&tq, base, DP, L, BH, DP, static_cast<uint64_t>(L) * DP, 64, BQ);
+  int rc = make_tmap_3d_f16(&tq, qh, DP, Lq, BH, DP, static_cast<uint64_t>(Lq) * DP, 64, BQ);
   if (rc) return rc;
-  rc = make_tmap_3d_f16(&tk, base + which_stride, DP, L, BH, DP, static_cast<uint64_t>(L) * DP, 64, bkv);
+  rc = make_tmap_3d_f16(&tk, kh, DP, L, BH, DP, static_cast<uint64_t>(L) * DP, 64, bkv);
   if (rc) return rc;
-  rc = make_tmap_3d_f16(&tv, base + 2 * which_stride, DP, L, BH, DP, static_cast<uint64_t>(L) * DP, 64, bkv);
+  rc = make_tmap_3d_f16(&tv, vh, DP, L, BH, DP, static_cast<uint64_t>(L) * DP, 64, bkv);
   if (rc) return rc;
   int sms = 0, per_sm = 1;
   rc = gemm::device_sms(&sms);
@@ -650,11 +661,11 @@ int launch_fa_impl(const void* qkvh, __half* o, void* part_ws, int B, int L, int
   const int slots = sms * per_sm;
 
   FaParams p;
-  p.L = L; p.H = H; p.d = d; p.C = C;
+  p.L = L; p.Lq = Lq; p.H = H; p.d = d; p.C = C;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.o = o;
   p.qk_shared = qk_shared;
-  p.n_qtiles = (L + BQ - 1) / BQ;
+  p.n_qtiles = (Lq + BQ - 1) / BQ;
   // Every tile costs the same, so the grid runs in waves of `slots` CTAs and the last, partial wave leaves most of
   // the GPU idle for a whole tile time.  The tiles of that wave are cut into `splits` key ranges instead (chosen to
   // minimise the time of the remainder, ceil(R * S / slots) / S tile times) and merged by fa_combine_kernel.
@@ -695,12 +706,24 @@ int launch_fa_impl(const void* qkvh, __half* o, void* part_ws, int B, int L, int
 }
 
 template <int KSTEPS>
-int launch_fa(const void* qkvh, __half* o, void* part_ws, int B, int L, int C, int H, int d, float scale,
-              int qk_shared, cudaStream_t stream) {
+int launch_fa(const void* qh, const void* kh, const void* vh, __half* o, void* part_ws, int B, int Lq, int L, int C, int H,
+              int d, float scale, int qk_shared, cudaStream_t stream) {
 #if !defined(VTM_FA_NO_ONES)   // A/B switch: keep the denominator in the softmax warps
-  if (d % 16 == 8) return launch_fa_impl<KSTEPS, true>(qkvh, o, part_ws, B, L, C, H, d, scale, qk_shared, stream);
+  if (d % 16 == 8)
+    return launch_fa_impl<KSTEPS, true>(qh, kh, vh, o, part_ws, B, Lq, L, C, H, d, scale, qk_shared, stream);
 #endif
-  return launch_fa_impl<KSTEPS, false>(qkvh, o, part_ws, B, L, C, H, d, scale, qk_shared, stream);
+  return launch_fa_impl<KSTEPS, false>(qh, kh, vh, o, part_ws, B, Lq, L, C, H, d, scale, qk_shared, stream);
+}
+
+int launch_fa_any(const void* qh, const void* kh, const void* vh, __half* o, void* part_ws, int B, int Lq, int L, int C,
+                  int H, int d, float scale, int qk_shared, cudaStream_t stream) {
+  switch ((d + 15) / 16) {
+    case 1: case 2: case 3: return launch_fa<3>(qh, kh, vh, o, part_ws, B, Lq, L, C, H, d, scale, qk_shared, stream);
+    case 4: return launch_fa<4>(qh, kh, vh, o, part_ws, B, Lq, L, C, H, d, scale, qk_shared, stream);
+    case 5: return launch_fa<5>(qh, kh, vh, o, part_ws, B, Lq, L, C, H, d, scale, qk_shared, stream);
+    case 6: return launch_fa<6>(qh, kh, vh, o, part_ws, B, Lq, L, C, H, d, scale, qk_shared, stream);
+    default: return launch_fa<8>(qh, kh, vh, o, part_ws, B, Lq, L, C, H, d, scale, qk_shared, stream);
+  }
 }
 
 }  // namespace
@@ -735,15 +758,9 @@ extern "C" int vtm_attention_ex(const void* x_dev, const void* w_qkv_dev, const 
       (reinterpret_cast<uintptr_t>(o + static_cast<size_t>(M) * C) + 255u) & ~static_cast<uintptr_t>(255u));
   int rc = launch_qkv_heads(x_dev, w_qkv_dev, qkv, B, L, C, heads, DP, stream);
   if (rc) return rc;
-  const int ksteps = (d + 15) / 16;
-  const int shared = flags & 1;
-  switch (ksteps) {
-    case 1: case 2: case 3: rc = launch_fa<3>(qkv, o, part_ws, B, L, C, heads, d, scale, shared, stream); break;
-    case 4: rc = launch_fa<4>(qkv, o, part_ws, B, L, C, heads, d, scale, shared, stream); break;
-    case 5: rc = launch_fa<5>(qkv, o, part_ws, B, L, C, heads, d, scale, shared, stream); break;
-    case 6: rc = launch_fa<6>(qkv, o, part_ws, B, L, C, heads, d, scale, shared, stream); break;
-    default: rc = launch_fa<8>(qkv, o, part_ws, B, L, C, heads, d, scale, shared, stream); break;
-  }
+  const __half* kh = qkv + static_cast<size_t>(B) * heads * L * DP;
+  const __half* vh = kh + static_cast<size_t>(B) * heads * L * DP;
+  rc = launch_fa_any(qkv, kh, vh, o, part_ws, B, L, L, C, heads, d, scale, flags & 1, stream);
   if (rc) return rc;
   return vtm_linear_f16(o, w_o_dev, b_o_dev, M, C, C, y_dev, C, stream_);
 }
@@ -752,4 +769,45 @@ extern "C" int vtm_attention(const void* x_dev, const void* w_qkv_dev, const voi
                              int32_t B, int32_t L, int32_t C, int32_t heads, float scale, void* y_dev,
                              void* ws_dev, size_t ws_bytes, void* stream_) {
   return vtm_attention_ex(x_dev, w_qkv_dev, w_o_dev, b_o_dev, B, L, C, heads, scale, 0, y_dev, ws_dev, ws_bytes, stream_);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Cross-attention of the patched block (vidtome/patch.py:171-185: `self.attn2(norm2(h), encoder_hidden_states=ctx)` and
+// the residual add) — diffusers Attention with K/V from the text context.
+extern "C" size_t vtm_cross_attention_workspace_bytes(int32_t B, int32_t Lq, int32_t Lk, int32_t C, int32_t heads) {
+  if (B <= 0 || Lq <= 0 || Lk <= 0 || C <= 0 || heads <= 0 || C % heads != 0) return 0;
+  const int d = C / heads;
+  const size_t DP = d <= 64 ? 64 : 128;
+  return (static_cast<size_t>(B) * heads * (static_cast<size_t>(Lq) + 2 * static_cast<size_t>(Lk)) * DP +
+          static_cast<size_t>(B) * Lq * C) * 2 + vtm::FA_PART_BYTES + 512;
+}
+
+extern "C" int vtm_cross_attention(const void* x_dev, const void* ctx_dev, const void* w_q_dev, const void* w_kv_dev,
+                                   const void* w_o_dev, const void* b_o_dev, const void* resid_dev, int32_t B, int32_t Lq,
+                                   int32_t Lk, int32_t C, int32_t Cctx, int32_t heads, float scale, void* y_dev,
+                                   void* ws_dev, size_t ws_bytes, void* stream_) {
+  using namespace vtm;
+  if (!x_dev || !ctx_dev || !w_q_dev || !w_kv_dev || !w_o_dev || !y_dev || !ws_dev) return VTM_E_NULL;
+  if (B <= 0 || Lq <= 0 || Lk <= 0 || C <= 0 || Cctx <= 0 || heads <= 0 || C % heads != 0) return VTM_E_SHAPE;
+  const int d = C / heads;
+  if (d % 8 != 0 || C % 8 != 0 || Cctx % 8 != 0) return VTM_E_SHAPE;
+  if (d > 128) return VTM_E_UNSUPPORTED;
+  if (ws_bytes < vtm_cross_attention_workspace_bytes(B, Lq, Lk, C, heads)) return VTM_E_WS;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int DP = d <= 64 ? 64 : 128;
+  __half* qh = static_cast<__half*>(ws_dev);
+  __half* kh = qh + static_cast<size_t>(B) * heads * Lq * DP;
+  __half* vh = kh + static_cast<size_t>(B) * heads * Lk * DP;
+  __half* o = vh + static_cast<size_t>(B) * heads * Lk * DP;
+  void* part_ws = reinterpret_cast<void*>(
+      (reinterpret_cast<uintptr_t>(o + static_cast<size_t>(B) * Lq * C) + 255u) & ~static_cast<uintptr_t>(255u));
+  int rc = launch_head_proj(x_dev, w_q_dev, qh, B, Lq, C, C, heads, DP, 0, 1, stream);
+  if (rc) return rc;
+  rc = launch_head_proj(ctx_dev, w_kv_dev, kh, B, Lk, Cctx, C, heads, DP, 1, 2, stream);
+  if (rc) return rc;
+  rc = launch_fa_any(qh, kh, vh, o, part_ws, B, Lq, Lk, C, heads, d, scale, 0, stream);
+  if (rc) return rc;
+  const int M = B * Lq;
+  if (resid_dev) return vtm_linear_residual_f16(o, w_o_dev, b_o_dev, resid_dev, C, M, C, C, y_dev, C, stream_);
+  return vtm_linear_f16(o, w_o_dev, b_o_dev, M, C, C, y_dev, C, stream_);
 }

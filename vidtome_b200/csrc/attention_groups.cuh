@@ -353,8 +353,8 @@ flash_attn_groups_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
         }
       }
       if (nparts == 1) {
-        if (row < p.L) {
-          __half* orow = p.o + (static_cast<size_t>(b) * p.L + row) * p.C + h * p.d;
+        if (row < p.Lq) {
+          __half* orow = p.o + (static_cast<size_t>(b) * p.Lq + row) * p.C + h * p.d;
 #pragma unroll
           for (int gq = 0; gq < 2; ++gq) {
             if (cb + gq * 8 < p.d) {

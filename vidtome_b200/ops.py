@@ -358,6 +358,33 @@ def attention(x: torch.Tensor, w_qkv: torch.Tensor, w_o: torch.Tensor, b_o: Opti
     return y
 
 
+def cross_attention(x: torch.Tensor, ctx: torch.Tensor, w_q: torch.Tensor, w_kv: torch.Tensor, w_o: torch.Tensor,
+                    b_o: Optional[torch.Tensor], heads: int, scale: float, resid: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """attn2 of the block: x [B, Lq, C] queries, ctx [B, Lk, Cctx] keys/values; returns o Wo^T + bo (+ resid)."""
+    _require(x, torch.float16, "x")
+    _require(ctx, torch.float16, "ctx")
+    _require(w_q, torch.float16, "w_q")
+    _require(w_kv, torch.float16, "w_kv")
+    _require(w_o, torch.float16, "w_o")
+    B, Lq, Cc = x.shape
+    Lk, Cctx = ctx.shape[1], ctx.shape[2]
+    if ctx.shape[0] != B:
+        raise RuntimeError("cross_attention: x and ctx must have the same number of items")
+    if resid is not None:
+        _require(resid, torch.float16, "resid")
+    lib = _lib.load()
+    ws_bytes = lib.vtm_cross_attention_workspace_bytes(B, Lq, Lk, Cc, heads)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    y = torch.empty_like(x)
+    flops = 4.0 * B * Lq * Lk * Cc + 4.0 * B * Lq * Cc * Cc + 4.0 * B * Lk * Cctx * Cc
+    with _Timed("XA", flops, 2.0 * B * Lq * Cc * (3 if resid is not None else 2)):
+        check(lib.vtm_cross_attention(x.data_ptr(), ctx.data_ptr(), w_q.data_ptr(), w_kv.data_ptr(), w_o.data_ptr(), _ptr(b_o),
+                                      _ptr(resid), B, Lq, Lk, Cc, Cctx, heads, float(scale), y.data_ptr(), ws.data_ptr(),
+                                      ws_bytes, _stream()), "vtm_cross_attention")
+    STATS.launches += 4
+    return y
+
+
 def keys_to_score_arg(keys: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """Unpack KA keys on the device with torch integer ops (test / debugging helper)."""
     o = (keys >> 32) & 0xFFFF

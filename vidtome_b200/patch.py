@@ -55,6 +55,8 @@ FUSE_LAYERNORM = True
 
 # Run a stock GEGLU feed-forward (norm3 + ff + residual, patch.py:187-199) through the tcgen05 kernels (feedforward.py).
 FUSE_FEED_FORWARD = True
+# Run a stock cross-attention (norm2 + attn2 + residual, patch.py:171-185) through the CUDA library (attention.py).
+FUSE_CROSS_ATTENTION = True
 
 # How `merge_global=True` obtains the global token set when several ranks each hold one chunk:
 #   "recurrence" — the reference's semantics (patch.py:59-82): whatever the previous chunk processed by THIS
@@ -308,7 +310,20 @@ def make_diffusers_tome_block(block_class: Type[torch.nn.Module]) -> Type[torch.
             else:
                 hidden_states = attn_output + hidden_states
 
-            if getattr(self, "attn2", None) is not None:                     # patch.py:171-185
+            attn2 = getattr(self, "attn2", None)
+            if (attn2 is not None and FUSE_CROSS_ATTENTION and hidden_states.is_cuda and not self.use_ada_layer_norm
+                    and encoder_attention_mask is None and not cross_attention_kwargs
+                    and _attention.cross_attention_eligible(attn2, encoder_hidden_states)
+                    and encoder_hidden_states.shape[0] == hidden_states.shape[0]):
+                ln2 = _fusable_layer_norm(self.norm2, hidden_states)
+                if ln2 is not None:
+                    # norm2 -> q / kv projections (head-major) -> flash attention over the context -> out projection
+                    # with bias and residual fused (patch.py:171-185), all in the CUDA library
+                    shape = hidden_states.shape
+                    n2 = ops.layer_norm(hidden_states.contiguous().view(-1, shape[-1]), ln2).view(shape)
+                    hidden_states = _attention.cross_attention_residual(attn2, n2, encoder_hidden_states, hidden_states)
+                    attn2 = None
+            if attn2 is not None:                                            # patch.py:171-185
                 norm_hidden_states = (self.norm2(hidden_states, timestep) if self.use_ada_layer_norm
                                       else self.norm2(hidden_states))
                 attn_output = self.attn2(norm_hidden_states, encoder_hidden_states=encoder_hidden_states,
