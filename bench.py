@@ -241,7 +241,7 @@ def ka_traffic():
         return None
 
 
-def comparators(torch, net, dev, steps, kind):
+def comparators(torch, net, dev, steps, kind, cond=None):
     """Same-GPU, same-process comparators (N=1).  `net` arrives unpatched."""
     import vidtome_b200
     from types import SimpleNamespace
@@ -252,7 +252,7 @@ def comparators(torch, net, dev, steps, kind):
 
     # ---- (i) the reference's GPU formulation of the whole step
     R.apply_reference_path(net, RATIO, 2)
-    den = ChunkedDenoiser(net, n_timesteps=50, chunk_size=FRAMES)
+    den = ChunkedDenoiser(net, n_timesteps=50, chunk_size=FRAMES, cond=cond)
     g = torch.Generator(device=dev).manual_seed(123)
     x = torch.randn((FRAMES, 4, LATENT, LATENT), generator=g, device=dev, dtype=torch.float16)
     for i in range(2):
@@ -504,7 +504,7 @@ def run_ours(args):
             out["c4_global"] = c4
         if world == 1 and not args.no_gpu_ref:
             vidtome_b200.remove_patch(net)
-            out["comparators"] = comparators(torch, net, dev, args.steps, kind)
+            out["comparators"] = comparators(torch, net, dev, args.steps, kind, cond)
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             ds1, ds2 = cpu_torch_block_calls(cores)

@@ -179,8 +179,10 @@ def test_cross_attention_matches_fp32_reference(B, Lq, Lk, C, Cctx, heads):
 
 
 def test_full_block_fast_paths_match_module_paths():
-    """A full patched block (self-attention section + cross-attention + GEGLU feed-forward) with every fast path on
-    equals the same block with attn2 / ff running through their torch modules (FUSE_* switches off)."""
+    """Full blocks (self-attention + cross-attention + GEGLU feed-forward) with the attn2 / ff fast paths on equal the
+    same blocks with attn2 / ff running through their torch modules (FUSE_* switches off).  max_downsample=0 keeps the
+    merge out of the comparison: through several blocks a 1e-3 difference would otherwise flip last-bit ties of LATER
+    blocks' matches and turn a numerics check into a decision check (those are covered by the parity tests)."""
     import vidtome_b200
     from vidtome_b200 import patch
     from vidtome_b200.skeleton import make_skeleton
@@ -189,7 +191,7 @@ def test_full_block_fast_paths_match_module_paths():
         patch.FUSE_CROSS_ATTENTION = patch.FUSE_FEED_FORWARD = fast
         try:
             net = make_skeleton("tiny", device="cuda", hot_path_only=False, seed=11)
-            vidtome_b200.apply_patch(net, batch_size=2, local_merge_ratio=1.0)
+            vidtome_b200.apply_patch(net, batch_size=2, max_downsample=0)
             torch.manual_seed(2); torch.cuda.manual_seed(2)
             lat = torch.randn(2 * 4, 4, 16, 16, device="cuda", dtype=torch.float16)
             ctx = torch.randn(2 * 4, 77, 768, device="cuda", dtype=torch.float16)
