@@ -30,13 +30,15 @@ struct StoreEpi {
       uint32_t pk[32];
       const int c0 = col0 + cb;
 #pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        float f0 = __uint_as_float(r[2 * e]), f1 = __uint_as_float(r[2 * e + 1]);
-        if (bias && c0 + 2 * e < N) {          // N % 8 == 0
-          f0 += __half2float(bias[c0 + 2 * e]);
-          f1 += __half2float(bias[c0 + 2 * e + 1]);
+      for (int v8 = 0; v8 < 8; ++v8) {         // eight columns at a time: one 16-byte bias load (N % 8 == 0)
+        uint4 bv = make_uint4(0, 0, 0, 0);
+        if (bias && c0 + 8 * v8 < N) bv = __ldg(reinterpret_cast<const uint4*>(bias + c0 + 8 * v8));
+        const __half2* b2 = reinterpret_cast<const __half2*>(&bv);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 bf = __half22float2(b2[e]);
+          pk[4 * v8 + e] = pack_f16x2(__uint_as_float(r[8 * v8 + 2 * e]) + bf.x, __uint_as_float(r[8 * v8 + 2 * e + 1]) + bf.y);
         }
-        pk[e] = pack_f16x2(f0, f1);
       }
       // store phase: this lane writes columns [c, c + 8) of rows row0 + lane / 8 + 4 i
       const int c = c0 + (threadIdx.x & 7) * 8;
@@ -65,24 +67,26 @@ struct StoreEpi {
   __device__ __forceinline__ void end(int, int, int) {}
 };
 
-// erf via Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below fp16 resolution): two MUFU ops + 8 FMA-pipe ops.
-__device__ __forceinline__ float erf_as(float x) {
-  const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  p *= t;
-  const float e = ex2_approx(-1.4426950408889634f * ax * ax);
-  return copysignf(fmaf(-p, e, 1.f), x);
+// gelu(g) = 0.5 g (1 + erf(g / sqrt 2)) with ONE MUFU op: for z = |g| / sqrt 2, log2(erfc(z)) is smooth and close to a
+// parabola, so h = erfc(z) / 2 = 2^(p(z) - 1) with a degree-5 polynomial p (p(0) = 0; fitted for minimal error of erf on
+// [0, 4.2]: |erf error| <= 6e-7, |gelu error| <= 1.1e-6 — four orders below fp16 resolution), z clamped at 4.2
+// (erfc(4.2) = 3e-9).  Then gelu(g) = g (1 - h) for g >= 0 and g h for g < 0.  Evaluated on packed lanes (two values).
+__device__ __forceinline__ void gelu_x2(float g0, float g1, float& y0, float& y1) {
+  const float z0 = fminf(fabsf(g0) * 0.7071067811865476f, 4.2f), z1 = fminf(fabsf(g1) * 0.7071067811865476f, 4.2f);
+  const uint64_t z2 = f32x2_pack(z0, z1);
+  uint64_t p2 = f32x2_fma(f32x2_pack(-0.00294415686f, -0.00294415686f), z2, f32x2_pack(0.0295900391f, 0.0295900391f));
+  p2 = f32x2_fma(p2, z2, f32x2_pack(-0.148665626f, -0.148665626f));
+  p2 = f32x2_fma(p2, z2, f32x2_pack(-0.918509366f, -0.918509366f));
+  p2 = f32x2_fma(p2, z2, f32x2_pack(-1.62788901f, -1.62788901f));
+  p2 = f32x2_fma(p2, z2, f32x2_pack(-1.f, -1.f));                      // p(z) - 1
+  float p0, p1;
+  f32x2_unpack(p2, p0, p1);
+  const float h0 = ex2_approx(p0), h1 = ex2_approx(p1);                 // erfc(z) / 2
+  const float gh0 = g0 * h0, gh1 = g1 * h1;
+  y0 = g0 >= 0.f ? g0 - gh0 : gh0;
+  y1 = g1 >= 0.f ? g1 - gh1 : gh1;
 }
 
-// GEGLU epilogue (diffusers GEGLU: `h, gate = proj(x).chunk(2, -1); h * gelu(gate)`, the first layer of the
-// feed-forward the reference block calls at vidtome/patch.py:187-199).  The weight rows are interleaved on the host in
-// groups of 32 ([a 0..31 | gate 0..31 | a 32..63 | gate 32..63 | ...]) so that an epilogue thread finds a value and its
-// gate in the same 64-column TMEM load; the output has N/2 columns.  Roundings follow torch's fp16 pipeline: proj output
-// -> fp16, gelu(gate) (erf form, evaluated in fp32) -> fp16, product -> fp16.
 struct GegluEpi {
   static constexpr uint32_t SCRATCH_PER_WARP = gemm::STAGE_STORE_BYTES;
   __half* d;             // [M, N/2]
@@ -108,21 +112,29 @@ struct GegluEpi {
         tmem_ld_wait();
         const int c0 = col0 + cb + 64 * hlf;
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          float a0 = __uint_as_float(r[2 * e]), a1 = __uint_as_float(r[2 * e + 1]);
-          float g0 = __uint_as_float(r[32 + 2 * e]), g1 = __uint_as_float(r[32 + 2 * e + 1]);
+        for (int v8 = 0; v8 < 4; ++v8) {       // eight values + their eight gates at a time: two 16-byte bias loads
+          uint4 ba = make_uint4(0, 0, 0, 0), bg = ba;
           if (bias && c0 < N) {
-            a0 += __half2float(bias[c0 + 2 * e]);
-            a1 += __half2float(bias[c0 + 2 * e + 1]);
-            g0 += __half2float(bias[c0 + 32 + 2 * e]);
-            g1 += __half2float(bias[c0 + 32 + 2 * e + 1]);
+            ba = __ldg(reinterpret_cast<const uint4*>(bias + c0 + 8 * v8));
+            bg = __ldg(reinterpret_cast<const uint4*>(bias + c0 + 32 + 8 * v8));
           }
-          // fp16 roundings of the unfused pipeline
-          a0 = __half2float(__float2half_rn(a0)); a1 = __half2float(__float2half_rn(a1));
-          g0 = __half2float(__float2half_rn(g0)); g1 = __half2float(__float2half_rn(g1));
-          const float q0 = __half2float(__float2half_rn(0.5f * g0 * (1.f + erf_as(g0 * 0.7071067811865476f))));
-          const float q1 = __half2float(__float2half_rn(0.5f * g1 * (1.f + erf_as(g1 * 0.7071067811865476f))));
-          pk[16 * hlf + e] = pack_f16x2(a0 * q0, a1 * q1);
+          const __half2* ba2 = reinterpret_cast<const __half2*>(&ba);
+          const __half2* bg2 = reinterpret_cast<const __half2*>(&bg);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i = 8 * v8 + 2 * e;
+            const float2 fa = __half22float2(ba2[e]), fg = __half22float2(bg2[e]);
+            // fp16 roundings of the unfused pipeline: projection output, gelu output, product
+            const uint32_t a16 = pack_f16x2(__uint_as_float(r[i]) + fa.x, __uint_as_float(r[i + 1]) + fa.y);
+            const uint32_t g16 = pack_f16x2(__uint_as_float(r[32 + i]) + fg.x, __uint_as_float(r[32 + i + 1]) + fg.y);
+            const float2 af = __half22float2(*reinterpret_cast<const __half2*>(&a16));
+            const float2 gf = __half22float2(*reinterpret_cast<const __half2*>(&g16));
+            float q0, q1;
+            gelu_x2(gf.x, gf.y, q0, q1);
+            const uint32_t q16 = pack_f16x2(q0, q1);
+            const float2 qf = __half22float2(*reinterpret_cast<const __half2*>(&q16));
+            pk[16 * hlf + 4 * v8 + e] = pack_f16x2(af.x * qf.x, af.y * qf.y);
+          }
         }
       }
       const int oc0 = (col0 + cb) >> 1;                       // first output column of this 64-wide store
