@@ -434,7 +434,7 @@ def run_ours(args):
     # per-kernel pass: eager stepping with every hot kernel bracketed by CUDA events on the launching stream
     n_k = max(2, min(args.steps, 5))
     eager_step(0)
-    ops.STATS.reset(timed=("KA", "KD", "K0", "KC", "KE", "KB1"))
+    ops.STATS.reset(timed=("KA", "KD", "K0", "KC", "KE", "KB1", "FF1", "FF2", "XA"))
     ms_eager = timed(eager_step, n_k)
     launches_per_step = ops.STATS.launches / n_k
     events = dict(ops.STATS.events)
@@ -467,7 +467,10 @@ def run_ours(args):
                                    ("K0", "hbm", "normalize_split_kernel (+ fused LayerNorm)"),
                                    ("KC", "hbm", "gather_rows_kernel (merge gather, + fused LayerNorm)"),
                                    ("KE", "hbm", "gather_rows_kernel<ADD> (unmerge + residual)"),
-                                   ("KB1", "hbm", "radix_sort_fused_kernel (latency-bound: 3 grid barriers)")):
+                                   ("KB1", "hbm", "radix_sort_fused_kernel (latency-bound: 3 grid barriers)"),
+                                   ("FF1", "tensor", "gemm_kernel<256, GegluEpi> (GEGLU projection, gate fused)"),
+                                   ("FF2", "tensor", "gemm_kernel<StoreEpi> (feed-forward output projection + bias + residual)"),
+                                   ("XA", "hbm", "vtm_cross_attention: q / kv projections + flash over 77 keys + out projection (+residual)")):
             t, fl, by, n = summarise(name)
             if n == 0 or t <= 0:
                 continue
@@ -476,7 +479,8 @@ def run_ours(args):
                 others[name] = {"bound": "tensor", "kernel": label, "achieved": round(a, 1), "peak": pk["tf_burst"],
                                 "unit": "TFLOP/s", "frac": round(a / pk["tf_burst"], 3), "launches": n,
                                 "ms_per_step": round(t / n_k, 4), "share_of_step": round(t / ms_eager, 3),
-                                "note": "head_dim 40/80: the softmax exponentials (MUFU) bound this kernel before the tensor pipe does"}
+                                "note": ("head_dim 40/80: the softmax exponentials (MUFU) bound this kernel before the tensor pipe does"
+                                         if name == "KD" else "tcgen05 GEMM with a fused epilogue")}
             else:
                 a = by / t / 1e6
                 others[name] = {"bound": "hbm", "kernel": label, "achieved": round(a, 1), "peak": pk["hbm"], "unit": "GB/s",
