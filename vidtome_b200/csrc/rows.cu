@@ -45,19 +45,34 @@ struct LnParams {
   float eps;
 };
 
-// In-register LayerNorm of one row held as P vectors per lane by a G-lane group (torch half semantics).
+// In-register LayerNorm of one row held as P vectors per lane by a G-lane group (torch half semantics: fp32
+// statistics, y = gamma * (rstd * (x - mean)) + beta in fp32, rounded to fp16).  The kernels that fuse it are bound by
+// instruction issue, not by HBM (r01: 0.45-0.49 of the copy bandwidth), so the row is converted to fp32 ONCE and kept in
+// registers through both statistics passes and the affine step, and gamma / beta are read as fp32 from shared memory
+// (staged once per CTA by stage_ln_params) instead of two 16-byte global loads + 16 conversions per data vector.
+constexpr int LN_MAX_C = 2048;
+__device__ __forceinline__ void stage_ln_params(const LnParams& ln, int C, float* s_gamma, float* s_beta) {
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    s_gamma[i] = __half2float(ln.w[i]);
+    s_beta[i] = ln.b ? __half2float(ln.b[i]) : 0.f;
+  }
+  __syncthreads();
+}
 template <int G, int P>
-__device__ __forceinline__ void layer_norm_row(uint4 (&v)[P], int sub, int vecs, int C, const LnParams& ln) {
+__device__ __forceinline__ void layer_norm_row(uint4 (&v)[P], int sub, int vecs, int C, float eps,
+                                               const float* __restrict__ s_gamma, const float* __restrict__ s_beta) {
+  float f[P][8];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < P; ++i) {
-    if (sub + G * i < vecs) {
-      const __half2* h = reinterpret_cast<const __half2*>(&v[i]);
+    const __half2* h = reinterpret_cast<const __half2*>(&v[i]);
+    const bool on = sub + G * i < vecs;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = __half22float2(h[e]);
-        s += f.x + f.y;
-      }
+    for (int e = 0; e < 4; ++e) {
+      const float2 t = __half22float2(h[e]);
+      f[i][2 * e] = on ? t.x : 0.f;
+      f[i][2 * e + 1] = on ? t.y : 0.f;
+      s += f[i][2 * e] + f[i][2 * e + 1];
     }
   }
   const float mean = group_sum<G>(s) / static_cast<float>(C);
@@ -65,33 +80,25 @@ __device__ __forceinline__ void layer_norm_row(uint4 (&v)[P], int sub, int vecs,
 #pragma unroll
   for (int i = 0; i < P; ++i) {
     if (sub + G * i < vecs) {
-      const __half2* h = reinterpret_cast<const __half2*>(&v[i]);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = __half22float2(h[e]);
-        q = fmaf(f.x - mean, f.x - mean, q);
-        q = fmaf(f.y - mean, f.y - mean, q);
+      for (int e = 0; e < 8; ++e) {
+        f[i][e] -= mean;
+        q = fmaf(f[i][e], f[i][e], q);
       }
     }
   }
-  const float rstd = rsqrtf(group_sum<G>(q) / static_cast<float>(C) + ln.eps);
+  const float rstd = rsqrtf(group_sum<G>(q) / static_cast<float>(C) + eps);
 #pragma unroll
   for (int i = 0; i < P; ++i) {
     const int vi = sub + G * i;
     if (vi < vecs) {
-      const uint4 gw = ld_16(ln.w + vi * 8);
-      uint4 gb = make_uint4(0, 0, 0, 0);
-      if (ln.b) gb = ld_16(ln.b + vi * 8);
+      const float4 g0 = *reinterpret_cast<const float4*>(s_gamma + vi * 8), g1 = *reinterpret_cast<const float4*>(s_gamma + vi * 8 + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(s_beta + vi * 8), b1 = *reinterpret_cast<const float4*>(s_beta + vi * 8 + 4);
       __half2* h = reinterpret_cast<__half2*>(&v[i]);
-      const __half2* w2 = reinterpret_cast<const __half2*>(&gw);
-      const __half2* b2 = reinterpret_cast<const __half2*>(&gb);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = __half22float2(h[e]);
-        const float2 wf = __half22float2(w2[e]);
-        const float2 bf = __half22float2(b2[e]);
-        h[e] = __floats2half2_rn(wf.x * (rstd * (f.x - mean)) + bf.x, wf.y * (rstd * (f.y - mean)) + bf.y);
-      }
+      h[0] = __floats2half2_rn(fmaf(g0.x, rstd * f[i][0], b0.x), fmaf(g0.y, rstd * f[i][1], b0.y));
+      h[1] = __floats2half2_rn(fmaf(g0.z, rstd * f[i][2], b0.z), fmaf(g0.w, rstd * f[i][3], b0.w));
+      h[2] = __floats2half2_rn(fmaf(g1.x, rstd * f[i][4], b1.x), fmaf(g1.y, rstd * f[i][5], b1.y));
+      h[3] = __floats2half2_rn(fmaf(g1.z, rstd * f[i][6], b1.z), fmaf(g1.w, rstd * f[i][7], b1.w));
     }
   }
 }
@@ -100,11 +107,14 @@ __device__ __forceinline__ void layer_norm_row(uint4 (&v)[P], int sub, int vecs,
 // merge.py:84 `metric = metric / metric.norm(dim=-1, keepdim=True)`; merge.py:76-85 split().
 // torch half semantics: norm accumulates in fp32 and is rounded to fp16; the division is carried out
 // in fp32 on the fp16-rounded norm and rounded to fp16.
-template <int G, int P>
-__global__ void __launch_bounds__(ROW_THREADS, 4)
+template <int G, int P, bool LN>
+__global__ void __launch_bounds__(ROW_THREADS, (LN && P > 3) ? 3 : 4)
 normalize_split_kernel(const __half* __restrict__ x, long long x_bs, const int* __restrict__ rowmap,
                        long long map_bs, Split sp, int B, int C, LnParams ln, __half* __restrict__ a_out,
                        __half* __restrict__ b_out) {
+  __shared__ __align__(16) float s_gamma[LN ? LN_MAX_C : 4];
+  __shared__ __align__(16) float s_beta[LN ? LN_MAX_C : 4];
+  if (LN) stage_ln_params(ln, C, s_gamma, s_beta);
   resolve_split(sp);
   constexpr int RPW = 32 / G;                       // rows per warp
   const int lane = threadIdx.x & 31;
@@ -139,7 +149,7 @@ normalize_split_kernel(const __half* __restrict__ x, long long x_bs, const int* 
       v[i] = make_uint4(0, 0, 0, 0);
       if (live && sub + G * i < vecs) v[i] = ld_nc_16(src + (sub + G * i) * 8);
     }
-    if (ln.w) layer_norm_row<G, P>(v, sub, vecs, C, ln);
+    if (LN) layer_norm_row<G, P>(v, sub, vecs, C, ln.eps, s_gamma, s_beta);
     float ss = 0.f;
 #pragma unroll
     for (int i = 0; i < P; ++i) {
@@ -193,11 +203,14 @@ struct PeerDsts {
   int n;
 };
 
-template <int G, int P, bool ADD>
-__global__ void __launch_bounds__(ROW_THREADS, 4)
+template <int G, int P, bool ADD, bool LN>
+__global__ void __launch_bounds__(ROW_THREADS, (LN && P > 3) ? 3 : 4)
 gather_rows_kernel(const __half* __restrict__ x, long long x_bs, const int* __restrict__ map, long long map_bs,
                    const __half* __restrict__ resid, int B, int L, int C, LnParams ln, __half* __restrict__ y,
                    long long y_bs, PeerDsts peers) {
+  __shared__ __align__(16) float s_gamma[LN ? LN_MAX_C : 4];
+  __shared__ __align__(16) float s_beta[LN ? LN_MAX_C : 4];
+  if (LN) stage_ln_params(ln, C, s_gamma, s_beta);
   constexpr int RPW = 32 / G;
   const int lane = threadIdx.x & 31;
   const int sub = lane % G, grp = lane / G;
@@ -233,7 +246,7 @@ gather_rows_kernel(const __half* __restrict__ x, long long x_bs, const int* __re
       v[k] = make_uint4(0, 0, 0, 0);
       if (live && sub + G * k < vecs) v[k] = ld_nc_16(src + (sub + G * k) * 8);
     }
-    if (!ADD && ln.w) layer_norm_row<G, P>(v, sub, vecs, C, ln);
+    if (LN) layer_norm_row<G, P>(v, sub, vecs, C, ln.eps, s_gamma, s_beta);
 #pragma unroll
     for (int i = 0; i < P; ++i) {
       if (live && sub + G * i < vecs) {
@@ -288,6 +301,13 @@ int grid_for_rows(K kernel, long long rows, int rows_per_warp, int sms) {
   else if ((vecs) <= 16 * 5) { CALL(16, 5) }        \
   else if ((vecs) <= 32 * 5) { CALL(32, 5) }        \
   else { CALL(32, 8) }
+// with the LayerNorm fused a lane also keeps its part of the row as fp32: at most 3 vectors (24 floats) per lane where
+// the row is short enough, so that the kernels keep 4 CTAs per SM
+#define VTM_DISPATCH_GP_LN(vecs, CALL)              \
+  if ((vecs) <= 16 * 3) { CALL(16, 3) }             \
+  else if ((vecs) <= 32 * 3) { CALL(32, 3) }        \
+  else if ((vecs) <= 32 * 5) { CALL(32, 5) }        \
+  else { CALL(32, 8) }
 
 }  // namespace
 }  // namespace vtm
@@ -301,7 +321,7 @@ extern "C" int vtm_normalize_split_ln(const void* x_dev, int64_t x_batch_stride,
   int rc = make_split(split, &sp);
   if (rc) return rc;
   if (!x_dev || (sp.Ns > 0 && !a_out_dev) || (sp.Nd > 0 && !b_out_dev)) return VTM_E_NULL;
-  if (B <= 0 || C <= 0 || (C % 8) != 0 || C > 32 * 8 * 8) return VTM_E_SHAPE;
+  if (B <= 0 || C <= 0 || (C % 8) != 0 || C > 32 * 8 * 8) return VTM_E_SHAPE;   // <= LN_MAX_C
   int sms = 0;
   rc = sm_count(&sms);
   if (rc) return rc;
@@ -309,13 +329,21 @@ extern "C" int vtm_normalize_split_ln(const void* x_dev, int64_t x_batch_stride,
   const int vecs = C / 8;
   LnParams ln{static_cast<const __half*>(ln_weight_dev), static_cast<const __half*>(ln_bias_dev), ln_eps};
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
-#define CALL(G, P)                                                                                          \
-  normalize_split_kernel<G, P>                                                                              \
-      <<<grid_for_rows(normalize_split_kernel<G, P>, rows, 32 / G, sms), ROW_THREADS, 0, st>>>(             \
+#define CALL_K0(G, P, LN)                                                                                   \
+  normalize_split_kernel<G, P, LN>                                                                          \
+      <<<grid_for_rows(normalize_split_kernel<G, P, LN>, rows, 32 / G, sms), ROW_THREADS, 0, st>>>(         \
           static_cast<const __half*>(x_dev), x_batch_stride, rowmap_dev, rowmap_batch_stride, sp, B, C, ln, \
           static_cast<__half*>(a_out_dev), static_cast<__half*>(b_out_dev));
-  VTM_DISPATCH_GP(vecs, CALL)
+  if (ln.w) {
+#define CALL(G, P) CALL_K0(G, P, true)
+    VTM_DISPATCH_GP_LN(vecs, CALL)
 #undef CALL
+  } else {
+#define CALL(G, P) CALL_K0(G, P, false)
+    VTM_DISPATCH_GP(vecs, CALL)
+#undef CALL
+  }
+#undef CALL_K0
   return launch_rc();
 }
 
@@ -348,13 +376,21 @@ extern "C" int vtm_gather_rows_peers(const void* x_dev, int64_t x_batch_stride, 
   const int vecs = C / 8;
   LnParams ln{static_cast<const __half*>(ln_weight_dev), static_cast<const __half*>(ln_bias_dev), ln_eps};
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
-#define CALL(G, P)                                                                                             \
-  gather_rows_kernel<G, P, false>                                                                              \
-      <<<grid_for_rows(gather_rows_kernel<G, P, false>, rows, 32 / G, sms), ROW_THREADS, 0, st>>>(             \
+#define CALL_KC(G, P, LN)                                                                                      \
+  gather_rows_kernel<G, P, false, LN>                                                                          \
+      <<<grid_for_rows(gather_rows_kernel<G, P, false, LN>, rows, 32 / G, sms), ROW_THREADS, 0, st>>>(         \
           static_cast<const __half*>(x_dev), x_batch_stride, map_dev, map_batch_stride, nullptr, B, L, C, ln,  \
           static_cast<__half*>(y_dev), y_batch_stride, peers);
-  VTM_DISPATCH_GP(vecs, CALL)
+  if (ln.w) {
+#define CALL(G, P) CALL_KC(G, P, true)
+    VTM_DISPATCH_GP_LN(vecs, CALL)
 #undef CALL
+  } else {
+#define CALL(G, P) CALL_KC(G, P, false)
+    VTM_DISPATCH_GP(vecs, CALL)
+#undef CALL
+  }
+#undef CALL_KC
   return launch_rc();
 }
 
@@ -390,16 +426,16 @@ extern "C" int vtm_unmerge_add(const void* y_dev, int64_t y_batch_stride, const 
   LnParams ln{nullptr, nullptr, 0.f};
   if (resid_dev) {
 #define CALL(G, P)                                                                                          \
-  gather_rows_kernel<G, P, true>                                                                            \
-      <<<grid_for_rows(gather_rows_kernel<G, P, true>, rows, 32 / G, sms), ROW_THREADS, 0, st>>>(           \
+  gather_rows_kernel<G, P, true, false>                                                                     \
+      <<<grid_for_rows(gather_rows_kernel<G, P, true, false>, rows, 32 / G, sms), ROW_THREADS, 0, st>>>(    \
           static_cast<const __half*>(y_dev), y_batch_stride, map_dev, map_batch_stride,                     \
           static_cast<const __half*>(resid_dev), B, N, C, ln, static_cast<__half*>(out_dev), out_bs, PeerDsts{});
     VTM_DISPATCH_GP(vecs, CALL)
 #undef CALL
   } else {
 #define CALL(G, P)                                                                                          \
-  gather_rows_kernel<G, P, false>                                                                           \
-      <<<grid_for_rows(gather_rows_kernel<G, P, false>, rows, 32 / G, sms), ROW_THREADS, 0, st>>>(          \
+  gather_rows_kernel<G, P, false, false>                                                                    \
+      <<<grid_for_rows(gather_rows_kernel<G, P, false, false>, rows, 32 / G, sms), ROW_THREADS, 0, st>>>(   \
           static_cast<const __half*>(y_dev), y_batch_stride, map_dev, map_batch_stride, nullptr, B, N, C, ln, \
           static_cast<__half*>(out_dev), out_bs, PeerDsts{});
     VTM_DISPATCH_GP(vecs, CALL)
