@@ -324,7 +324,7 @@ def c4_global_block(torch, dist, dev, rank, world, steps, timed):
     res = {"workload": "sd21_768_f8_chunk_per_gpu_local0.9_global0.8", "chunks": world, "frames_per_chunk": 8,
            "latent": [4, 96, 96], "exchange": {}}
     n = max(2, min(steps, 5))
-    for mode in ("allgather", "p2p"):
+    for mode in ("allgather", "p2p_all", "p2p"):
         patch.GLOBAL_EXCHANGE = mode
         try:
             den = ChunkedDenoiser(net, n_timesteps=50, chunk_size=8, merge_global=True)

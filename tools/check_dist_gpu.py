@@ -39,12 +39,13 @@ def main():
 
     # the same exchange fused into the merge gather (peer stores over NVLink + one barrier), three rounds so that both
     # alternating buffers and their reuse are exercised
-    patch.GLOBAL_EXCHANGE = "p2p"
     p2p_ok = True
-    for _ in range(3):
-        mod2 = SimpleNamespace(generator=gen(), global_tokens=None)
-        plan2 = patch.build_merge_plan(mod2, xs[rank], info(True))
-        p2p_ok &= torch.equal(plan2.merged_tokens, plan.merged_tokens) and torch.equal(plan2.pi, plan.pi)
+    for mode in ("p2p", "p2p_all"):
+        patch.GLOBAL_EXCHANGE = mode
+        for _ in range(3):
+            mod2 = SimpleNamespace(generator=gen(), global_tokens=None)
+            plan2 = patch.build_merge_plan(mod2, xs[rank], info(True))
+            p2p_ok &= torch.equal(plan2.merged_tokens, plan.merged_tokens) and torch.equal(plan2.pi, plan.pi)
 
     def timed(mode, n=20):
         patch.GLOBAL_EXCHANGE = mode

@@ -140,22 +140,25 @@ class PeerExchange:
             ex = cls._cache[key] = cls(B, L, C, device, group)
         return ex
 
-    def produce(self, table: torch.Tensor, mu: torch.Tensor, ln=None):
-        """Run KC for this rank's tokens into slot `rank` everywhere; returns (local tokens, tokens of rank-1)."""
+    def produce(self, table: torch.Tensor, mu: torch.Tensor, ln=None, everyone: bool = False):
+        """Run KC for this rank's tokens into slot `rank` of the consumer's buffer — rank k+1, the only rank that matches
+        against them — or, with `everyone`, of every rank's buffer (the all-gather semantics: 7x the NVLink
+        bytes on 8 GPUs for data nobody reads).  Returns (local tokens, tokens of rank-1)."""
         from . import ops
         ph = self.phase
         self.phase ^= 1
         mine = self.buf[ph, self.r]
         off = ((ph * self.w + self.r) * self.slot_elems) * 2                  # bytes from a buffer's base
-        peers = [int(self.hdl.buffer_ptrs[p]) + off for p in range(self.w) if p != self.r]
+        targets = [p for p in range(self.w) if p != self.r] if everyone else [(self.r + 1) % self.w]
+        peers = [int(self.hdl.buffer_ptrs[p]) + off for p in targets if p != self.r]
         ops.gather_rows_peers(table, mu, mine, peers, ln=ln)
         self.hdl.barrier(channel=ph)            # all ranks' stores of this block have landed
         return mine, self.buf[ph, (self.r - 1) % self.w]
 
 
-def exchange_fused(table: torch.Tensor, mu: torch.Tensor, ln=None, group=None):
-    """KC + exchange in one kernel (`patch.GLOBAL_EXCHANGE = "p2p"`): (local merged tokens, tokens of rank k-1)."""
+def exchange_fused(table: torch.Tensor, mu: torch.Tensor, ln=None, group=None, everyone: bool = False):
+    """KC + exchange in one kernel (`patch.GLOBAL_EXCHANGE = "p2p"` / `"p2p_all"`): (local merged tokens, tokens of rank k-1)."""
     B, L, C = table.shape[0], mu.shape[1], table.shape[2]
     ex = PeerExchange.get(B, L, C, table.device, group)
-    return ex.produce(table, mu, ln=ln)
+    return ex.produce(table, mu, ln=ln, everyone=everyone)
 

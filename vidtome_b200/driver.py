@@ -121,9 +121,9 @@ class ChunkedDenoiser:
             return chunks
         from . import dist as _dist
         chunks = _dist.shard_chunks(chunks)
-        if self.merge_global and patch.GLOBAL_EXCHANGE in ("allgather", "p2p") and _dist.world() > 1:
+        if self.merge_global and patch.GLOBAL_EXCHANGE in ("allgather", "p2p", "p2p_all") and _dist.world() > 1:
             uniform = _dist.check_step_lockstep([len(c) for c in chunks])
-            if not uniform and patch.GLOBAL_EXCHANGE == "p2p":
+            if not uniform and patch.GLOBAL_EXCHANGE in ("p2p", "p2p_all"):
                 raise RuntimeError("GLOBAL_EXCHANGE='p2p' needs equally long chunks on every rank (fixed chunking); "
                                    "use 'allgather' for ragged chunks")
         return chunks

@@ -62,7 +62,10 @@ FUSE_CROSS_ATTENTION = True
 #   "recurrence" — the reference's semantics (patch.py:59-82): whatever the previous chunk processed by THIS
 #                  process left in module.global_tokens;
 #   "allgather"  — chunk-per-GPU variant (option A): one NCCL all-gather of the local merged tokens
-#                  per merged block; rank k matches against the tokens of rank (k-1) mod G (dist.py).
+#                  per merged block; rank k matches against the tokens of rank (k-1) mod G (dist.py);
+#   "p2p"        — the same exchange fused into the kernel that produces the tokens: KC stores each merged row into
+#                  the peer-mapped buffer of its consumer, rank k+1, over NVLink (one barrier, no collective pass);
+#   "p2p_all"    — as "p2p" but into every rank's buffer (all-gather semantics; 7x the bytes on 8 GPUs).
 GLOBAL_EXCHANGE = "recurrence"
 
 
@@ -123,16 +126,18 @@ def build_merge_plan(module: torch.nn.Module, x: torch.Tensor, tome_info: Dict[s
         g = getattr(module, "global_tokens", None)
         exchanged = False
         local_tokens = None
-        if GLOBAL_EXCHANGE in ("allgather", "p2p"):
+        if GLOBAL_EXCHANGE in ("allgather", "p2p", "p2p_all"):
             from . import dist as _dist
             if _dist.world() > 1:
                 # "KF" = the merge gather together with the exchange (bench.py brackets it with CUDA events): bytes that
                 # cross NVLink per rank = (G - 1) * B * L * C * 2 in either mode
-                nvl = 2.0 * (_dist.world() - 1) * B * mu.shape[1] * C
+                fan = 1 if GLOBAL_EXCHANGE == "p2p" else _dist.world() - 1
+                nvl = 2.0 * fan * B * mu.shape[1] * C
                 with ops._Timed("KF", 0.0, nvl):
-                    if GLOBAL_EXCHANGE == "p2p":
-                        # KC stores the merged tokens into every rank's symmetric buffer: no separate collective pass
-                        local_tokens, g = _dist.exchange_fused(table, mu, ln=ln)
+                    if GLOBAL_EXCHANGE in ("p2p", "p2p_all"):
+                        # KC stores the merged tokens straight into the consumer's ("p2p": rank k+1) or every rank's
+                        # ("p2p_all") symmetric buffer: no separate collective pass
+                        local_tokens, g = _dist.exchange_fused(table, mu, ln=ln, everyone=GLOBAL_EXCHANGE == "p2p_all")
                     else:
                         local_tokens = ops.gather_rows(table, mu, ln=ln)
                         g = _dist.exchange_global_tokens(local_tokens)      # the one collective of this path
