@@ -47,8 +47,9 @@ struct LnParams {
 
 // In-register LayerNorm of one row held as P vectors per lane by a G-lane group (torch half semantics: fp32
 // statistics, y = gamma * (rstd * (x - mean)) + beta in fp32, rounded to fp16).  The kernels that fuse it are bound by
-// instruction issue, not by HBM (r01: 0.45-0.49 of the copy bandwidth), so the row is converted to fp32 ONCE and kept in
-// registers through both statistics passes and the affine step, and gamma / beta are read as fp32 from shared memory
+// instruction issue, not by HBM (r01: 0.45-0.49 of the copy bandwidth; a first r02 attempt with fewer rows per warp was
+// slower still: 0.42), so the row is converted to fp32 ONCE, kept in registers as packed pairs through both statistics
+// passes and the affine step, all arithmetic is packed (f32x2), and gamma / beta are read as fp32 from shared memory
 // (staged once per CTA by stage_ln_params) instead of two 16-byte global loads + 16 conversions per data vector.
 constexpr int LN_MAX_C = 2048;
 __device__ __forceinline__ void stage_ln_params(const LnParams& ln, int C, float* s_gamma, float* s_beta) {
@@ -58,47 +59,63 @@ __device__ __forceinline__ void stage_ln_params(const LnParams& ln, int C, float
   }
   __syncthreads();
 }
+__device__ __forceinline__ float f32x2_hsum(uint64_t a) {
+  float lo, hi;
+  f32x2_unpack(a, lo, hi);
+  return lo + hi;
+}
+// fp16x2 -> packed fp32 pair
+__device__ __forceinline__ uint64_t h2_to_f32x2(__half2 h) {
+  const float2 t = __half22float2(h);
+  return f32x2_pack(t.x, t.y);
+}
+__device__ __forceinline__ __half2 f32x2_to_h2(uint64_t a) {
+  float lo, hi;
+  f32x2_unpack(a, lo, hi);
+  return __floats2half2_rn(lo, hi);
+}
+// All arithmetic on PACKED fp32 pairs (add / mul / fma .f32x2: the same IEEE operations per lane at half the issue
+// slots, tools/ubench/fma2_pipe.cu).  The row lives in registers as P x 4 pairs.
 template <int G, int P>
 __device__ __forceinline__ void layer_norm_row(uint4 (&v)[P], int sub, int vecs, int C, float eps,
                                                const float* __restrict__ s_gamma, const float* __restrict__ s_beta) {
-  float f[P][8];
-  float s = 0.f;
+  uint64_t f[P][4];
+  uint64_t acc0 = 0, acc1 = 0;                         // (0.f, 0.f)
 #pragma unroll
   for (int i = 0; i < P; ++i) {
-    const __half2* h = reinterpret_cast<const __half2*>(&v[i]);
-    const bool on = sub + G * i < vecs;
+    const __half2* h = reinterpret_cast<const __half2*>(&v[i]);   // vectors beyond the row were loaded as zeros
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 t = __half22float2(h[e]);
-      f[i][2 * e] = on ? t.x : 0.f;
-      f[i][2 * e + 1] = on ? t.y : 0.f;
-      s += f[i][2 * e] + f[i][2 * e + 1];
-    }
+    for (int e = 0; e < 4; ++e) f[i][e] = h2_to_f32x2(h[e]);
+    acc0 = f32x2_add(acc0, f32x2_add(f[i][0], f[i][1]));
+    acc1 = f32x2_add(acc1, f32x2_add(f[i][2], f[i][3]));
   }
-  const float mean = group_sum<G>(s) / static_cast<float>(C);
-  float q = 0.f;
+  const float mean = group_sum<G>(f32x2_hsum(f32x2_add(acc0, acc1))) / static_cast<float>(C);
+  const uint64_t nm2 = f32x2_pack(-mean, -mean);
+  uint64_t q0 = 0, q1 = 0;
 #pragma unroll
   for (int i = 0; i < P; ++i) {
     if (sub + G * i < vecs) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        f[i][e] -= mean;
-        q = fmaf(f[i][e], f[i][e], q);
-      }
+      for (int e = 0; e < 4; ++e) f[i][e] = f32x2_add(f[i][e], nm2);
+      q0 = f32x2_fma(f[i][0], f[i][0], q0);
+      q1 = f32x2_fma(f[i][1], f[i][1], q1);
+      q0 = f32x2_fma(f[i][2], f[i][2], q0);
+      q1 = f32x2_fma(f[i][3], f[i][3], q1);
     }
   }
-  const float rstd = rsqrtf(group_sum<G>(q) / static_cast<float>(C) + eps);
+  const float rstd = rsqrtf(group_sum<G>(f32x2_hsum(f32x2_add(q0, q1))) / static_cast<float>(C) + eps);
+  const uint64_t r2 = f32x2_pack(rstd, rstd);
 #pragma unroll
   for (int i = 0; i < P; ++i) {
     const int vi = sub + G * i;
     if (vi < vecs) {
-      const float4 g0 = *reinterpret_cast<const float4*>(s_gamma + vi * 8), g1 = *reinterpret_cast<const float4*>(s_gamma + vi * 8 + 4);
-      const float4 b0 = *reinterpret_cast<const float4*>(s_beta + vi * 8), b1 = *reinterpret_cast<const float4*>(s_beta + vi * 8 + 4);
+      const ulonglong2 g0 = *reinterpret_cast<const ulonglong2*>(s_gamma + vi * 8), g1 = *reinterpret_cast<const ulonglong2*>(s_gamma + vi * 8 + 4);
+      const ulonglong2 b0 = *reinterpret_cast<const ulonglong2*>(s_beta + vi * 8), b1 = *reinterpret_cast<const ulonglong2*>(s_beta + vi * 8 + 4);
       __half2* h = reinterpret_cast<__half2*>(&v[i]);
-      h[0] = __floats2half2_rn(fmaf(g0.x, rstd * f[i][0], b0.x), fmaf(g0.y, rstd * f[i][1], b0.y));
-      h[1] = __floats2half2_rn(fmaf(g0.z, rstd * f[i][2], b0.z), fmaf(g0.w, rstd * f[i][3], b0.w));
-      h[2] = __floats2half2_rn(fmaf(g1.x, rstd * f[i][4], b1.x), fmaf(g1.y, rstd * f[i][5], b1.y));
-      h[3] = __floats2half2_rn(fmaf(g1.z, rstd * f[i][6], b1.z), fmaf(g1.w, rstd * f[i][7], b1.w));
+      h[0] = f32x2_to_h2(f32x2_fma(g0.x, f32x2_mul(r2, f[i][0]), b0.x));
+      h[1] = f32x2_to_h2(f32x2_fma(g0.y, f32x2_mul(r2, f[i][1]), b0.y));
+      h[2] = f32x2_to_h2(f32x2_fma(g1.x, f32x2_mul(r2, f[i][2]), b1.x));
+      h[3] = f32x2_to_h2(f32x2_fma(g1.y, f32x2_mul(r2, f[i][3]), b1.y));
     }
   }
 }
@@ -108,7 +125,7 @@ __device__ __forceinline__ void layer_norm_row(uint4 (&v)[P], int sub, int vecs,
 // torch half semantics: norm accumulates in fp32 and is rounded to fp16; the division is carried out
 // in fp32 on the fp16-rounded norm and rounded to fp16.
 template <int G, int P, bool LN>
-__global__ void __launch_bounds__(ROW_THREADS, (LN && P > 3) ? 3 : 4)
+__global__ void __launch_bounds__(ROW_THREADS, LN ? 3 : 4)
 normalize_split_kernel(const __half* __restrict__ x, long long x_bs, const int* __restrict__ rowmap,
                        long long map_bs, Split sp, int B, int C, LnParams ln, __half* __restrict__ a_out,
                        __half* __restrict__ b_out) {
@@ -150,41 +167,39 @@ normalize_split_kernel(const __half* __restrict__ x, long long x_bs, const int* 
       if (live && sub + G * i < vecs) v[i] = ld_nc_16(src + (sub + G * i) * 8);
     }
     if (LN) layer_norm_row<G, P>(v, sub, vecs, C, ln.eps, s_gamma, s_beta);
-    float ss = 0.f;
+    uint64_t ss0 = 0, ss1 = 0;
 #pragma unroll
     for (int i = 0; i < P; ++i) {
       const __half2* h = reinterpret_cast<const __half2*>(&v[i]);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = __half22float2(h[e]);
-        ss = fmaf(f.x, f.x, ss);
-        ss = fmaf(f.y, f.y, ss);
+      for (int e = 0; e < 4; e += 2) {
+        const uint64_t a = h2_to_f32x2(h[e]), c = h2_to_f32x2(h[e + 1]);
+        ss0 = f32x2_fma(a, a, ss0);
+        ss1 = f32x2_fma(c, c, ss1);
       }
     }
-    ss = group_sum<G>(ss);
+    const float ss = group_sum<G>(f32x2_hsum(f32x2_add(ss0, ss1)));
     const float nrm = __half2float(__float2half_rn(sqrtf(ss)));
     // x / nrm, correctly rounded, with ONE IEEE division per row: r = RN(1/nrm), q0 = RN(x r),
     // rem = x - q0 nrm (exact, FMA), q = RN(q0 + rem r) is RN(x / nrm) (Markstein) — checked exhaustively over
     // all fp16 numerators x 3000 fp16 norms in tests/test_host_cpu.py.  Sub-normal norms take the plain division.
     const bool fast = nrm >= 6.103515625e-05f;
     const float rinv = 1.0f / nrm;
+    const uint64_t rinv2 = f32x2_pack(rinv, rinv), nnrm2 = f32x2_pack(-nrm, -nrm);
 #pragma unroll
     for (int i = 0; i < P; ++i) {
       if (live && sub + G * i < vecs) {
         __half2* h = reinterpret_cast<__half2*>(&v[i]);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float2 f = __half22float2(h[e]);
-          float qx, qy;
           if (fast) {
-            const float q0x = __fmul_rn(f.x, rinv), q0y = __fmul_rn(f.y, rinv);
-            qx = __fmaf_rn(__fmaf_rn(-q0x, nrm, f.x), rinv, q0x);
-            qy = __fmaf_rn(__fmaf_rn(-q0y, nrm, f.y), rinv, q0y);
+            const uint64_t f2 = h2_to_f32x2(h[e]);
+            const uint64_t q0 = f32x2_mul(f2, rinv2);
+            h[e] = f32x2_to_h2(f32x2_fma(f32x2_fma(q0, nnrm2, f2), rinv2, q0));
           } else {
-            qx = f.x / nrm;
-            qy = f.y / nrm;
+            const float2 f = __half22float2(h[e]);
+            h[e] = __halves2half2(__float2half_rn(f.x / nrm), __float2half_rn(f.y / nrm));
           }
-          h[e] = __halves2half2(__float2half_rn(qx), __float2half_rn(qy));
         }
         st_16(dst + (sub + G * i) * 8, v[i]);
       }
@@ -204,7 +219,7 @@ struct PeerDsts {
 };
 
 template <int G, int P, bool ADD, bool LN>
-__global__ void __launch_bounds__(ROW_THREADS, (LN && P > 3) ? 3 : 4)
+__global__ void __launch_bounds__(ROW_THREADS, LN ? 3 : 4)
 gather_rows_kernel(const __half* __restrict__ x, long long x_bs, const int* __restrict__ map, long long map_bs,
                    const __half* __restrict__ resid, int B, int L, int C, LnParams ln, __half* __restrict__ y,
                    long long y_bs, PeerDsts peers) {
@@ -301,13 +316,8 @@ int grid_for_rows(K kernel, long long rows, int rows_per_warp, int sms) {
   else if ((vecs) <= 16 * 5) { CALL(16, 5) }        \
   else if ((vecs) <= 32 * 5) { CALL(32, 5) }        \
   else { CALL(32, 8) }
-// with the LayerNorm fused a lane also keeps its part of the row as fp32: at most 3 vectors (24 floats) per lane where
-// the row is short enough, so that the kernels keep 4 CTAs per SM
-#define VTM_DISPATCH_GP_LN(vecs, CALL)              \
-  if ((vecs) <= 16 * 3) { CALL(16, 3) }             \
-  else if ((vecs) <= 32 * 3) { CALL(32, 3) }        \
-  else if ((vecs) <= 32 * 5) { CALL(32, 5) }        \
-  else { CALL(32, 8) }
+// with the LayerNorm fused a lane also keeps its part of the row as packed fp32 (about 80 registers: 3 CTAs per SM)
+#define VTM_DISPATCH_GP_LN(vecs, CALL) VTM_DISPATCH_GP(vecs, CALL)
 
 }  // namespace
 }  // namespace vtm
