@@ -71,7 +71,7 @@ struct HeadSplitEpi {
       for (int e = 0; e < 32; ++e) pk[e] = pack_f16x2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
       // this lane's 8 columns in the store phase: the same for all of its rows
       const int n = col0 + cb + (threadIdx.x & 7) * 8;       // groups of 8 columns never straddle a head (d % 8 == 0)
-      const bool n_ok = n < n_proj * C;
+      const bool n_ok = n < n_proj * C && (threadIdx.x & 7) * 8 < ncols - cb;   // BN = 160: 16-column second chunk
       const int which = n / C, c = n - which * C;
       const int head = c / d, e0 = c - head * d;
       const bool last_group = e0 + 8 == d;                   // then this lane also zeroes the head's padding columns
@@ -116,9 +116,15 @@ int launch_head_proj(const void* x, const void* w, __half* out, int nb, int L, i
   CUtensorMap ta, tb;
   rc = make_tmap_3d_f16(&ta, x, K, M, 1, K, static_cast<uint64_t>(M) * K, gemm::BK, gemm::BM);
   if (rc) return rc;
+  gemm::Work wk;
+  if (N % 160 == 0 && N % 256 != 0 && N < 960) {     // N = 320 / 640 (q projection of the cross-attention): exact 160-wide tiles
+    rc = make_tmap_3d_f16(&tb, w, K, N, 1, K, static_cast<uint64_t>(N) * K, gemm::BK, 160);
+    if (rc) return rc;
+    wk.plan(M, N, K, 1, 160, sms, 16, 1);
+    return gemm::launch<160, HeadSplitEpi>(ta, tb, wk, epi, sms, stream);
+  }
   rc = make_tmap_3d_f16(&tb, w, K, N, 1, K, static_cast<uint64_t>(N) * K, gemm::BK, 128);
   if (rc) return rc;
-  gemm::Work wk;
   wk.plan(M, N, K, 1, 128, sms, 16, 1);
   return gemm::launch<128, HeadSplitEpi>(ta, tb, wk, epi, sms, stream);
 }

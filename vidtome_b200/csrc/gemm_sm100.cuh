@@ -12,7 +12,10 @@
 //
 // Epilogue policy `Epi` (all members __device__, called by every epilogue thread):
 //   void begin(int m_tile, int b, int row_in_tile);                  // new work item
-//   void tile(uint32_t taddr, int col0, int ncols);                  // this warp's 128-lane x (BN/2)-col
+//   void tile(uint32_t taddr, int col0, int ncols);                  // (ncols = BN/2 = 64, 80 or 128: policies that
+//                                                                    // support BN = 160 mask the 16-column tail of
+//                                                                    // their second 64-column chunk)
+//                                                                    // this warp's 128-lane x (BN/2)-col
 //                                                                    // slice of a finished accumulator:
 //                                                                    // taddr = TMEM address of (lane
 //                                                                    // quadrant, first column), col0 =
@@ -34,11 +37,12 @@ constexpr uint32_t A_BYTES = BM * BK * 2;
 
 template <int BN>
 struct Cfg {
-  static_assert(BN == 128 || BN == 256, "BN must be 128 or 256");
+  static_assert(BN == 128 || BN == 160 || BN == 256, "BN must be 128, 160 or 256");
   static constexpr uint32_t B_BYTES = BN * BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN == 256 ? 4 : 6;
-  static constexpr uint32_t TMEM_COLS = 2 * BN;
+  static constexpr int STAGES = BN == 256 ? 4 : (BN == 160 ? 5 : 6);
+  // two accumulators of BN columns; the allocation is rounded up to a power of two (320 -> 512 for BN = 160)
+  static constexpr uint32_t TMEM_COLS = 2 * BN <= 256 ? 256 : 512;
   static constexpr size_t SMEM_BYTES = 1024 + static_cast<size_t>(STAGES) * STAGE_BYTES + 256;
 };
 

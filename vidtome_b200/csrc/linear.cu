@@ -42,12 +42,13 @@ struct StoreEpi {
       }
       // store phase: this lane writes columns [c, c + 8) of rows row0 + lane / 8 + 4 i
       const int c = c0 + (threadIdx.x & 7) * 8;
+      const bool c_ok = c < N && (threadIdx.x & 7) * 8 < ncols - cb;     // BN = 160: the second chunk is 16 columns wide
       int row = row0 + ((threadIdx.x & 31) >> 3);
       __half* dst = d + static_cast<long long>(row) * ldd + c;
       const __half* rs = resid ? resid + static_cast<long long>(row) * ldr + c : nullptr;
       const long long row_step = 4 * ldd, rrow_step = 4 * ldr;
       gemm::warp_store_rows64(scratch, pk, [&](int, int, const uint4& v) {
-        if (row < M && c < N) {
+        if (row < M && c_ok) {
           uint4 o = v;
           if (rs) {
             const uint4 rv = *reinterpret_cast<const uint4*>(rs);
@@ -175,7 +176,15 @@ int linear_impl(const void* a_dev, const void* w_dev, const void* bias_dev, cons
   rc = make_tmap_3d_f16(&ta, a_dev, K, M, 1, K, static_cast<uint64_t>(M) * K, gemm::BK, gemm::BM);
   if (rc) return rc;
   gemm::Work wk;
-  // BN = 256 unless that leaves a mostly-empty last tile for narrow outputs
+  // Tile width: per k-chunk a CTA moves (128 + BN) rows of operands from L2 for 128 x BN outputs, and these GEMMs are
+  // bound by that traffic (K = 320 .. 1280), so the widest tile wins unless it leaves a mostly-empty last tile:
+  // N = 320 / 640 (output projections, feed-forward output) split exactly into 160-wide tiles.
+  if (N % 160 == 0 && N % 256 != 0 && N < 960) {
+    rc = make_tmap_3d_f16(&tb, w_dev, K, N, 1, K, static_cast<uint64_t>(N) * K, gemm::BK, 160);
+    if (rc) return rc;
+    wk.plan(M, N, K, 1, 160, sms, 16, 1);
+    return gemm::launch<160, StoreEpi>(ta, tb, wk, epi, sms, stream);
+  }
   const bool wide = (N % 256 == 0) || N >= 1024;
   if (wide) {
     rc = make_tmap_3d_f16(&tb, w_dev, K, N, 1, K, static_cast<uint64_t>(N) * K, gemm::BK, 256);
