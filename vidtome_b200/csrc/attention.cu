@@ -121,11 +121,13 @@ int launch_head_proj(const void* x, const void* w, __half* out, int nb, int L, i
     rc = make_tmap_3d_f16(&tb, w, K, N, 1, K, static_cast<uint64_t>(N) * K, gemm::BK, 160);
     if (rc) return rc;
     wk.plan(M, N, K, 1, 160, sms, 16, 1);
+    wk.n_fastest = 1;
     return gemm::launch<160, HeadSplitEpi>(ta, tb, wk, epi, sms, stream);
   }
   rc = make_tmap_3d_f16(&tb, w, K, N, 1, K, static_cast<uint64_t>(N) * K, gemm::BK, 128);
   if (rc) return rc;
   wk.plan(M, N, K, 1, 128, sms, 16, 1);
+  wk.n_fastest = 1;
   return gemm::launch<128, HeadSplitEpi>(ta, tb, wk, epi, sms, stream);
 }
 

@@ -52,8 +52,14 @@ struct Work {
   int tiles_per_split, n_splits;
   int k_chunks;
   int total;
+  // Order of the work items.  0: m tile fastest (KA: the dst ranges of one src block run far apart in time, so a later
+  // range starts from the maxima the earlier ones published).  1: n split fastest (plain GEMMs): the splits of one m tile
+  // run on neighbouring CTAs at the same time, so the A tile comes from HBM once and from L2 afterwards — with m fastest
+  // the feed-forward output projection (A = 335 MB > L2) read A from HBM once per n tile.
+  int n_fastest;
   __host__ void plan(int M, int N, int K, int B, int BN, int sms, int target_items_per_sm, int min_tiles) {
     batches = B;
+    n_fastest = 0;
     m_tiles = (M + BM - 1) / BM;
     n_tiles = (N + BN - 1) / BN;
     k_chunks = (K + BK - 1) / BK;
@@ -67,10 +73,18 @@ struct Work {
     total = static_cast<int>(base * n_splits);
   }
   __device__ __forceinline__ void decode(int w, int* m_tile, int* b, int* nt0, int* nt1) const {
-    *m_tile = w % m_tiles;
-    const int rest = w / m_tiles;
-    *b = rest % batches;
-    const int sp = rest / batches;
+    int sp;
+    if (n_fastest) {
+      sp = w % n_splits;
+      const int rest = w / n_splits;
+      *m_tile = rest % m_tiles;
+      *b = rest / m_tiles;
+    } else {
+      *m_tile = w % m_tiles;
+      const int rest = w / m_tiles;
+      *b = rest % batches;
+      sp = rest / batches;
+    }
     *nt0 = sp * tiles_per_split;
     const int e = *nt0 + tiles_per_split;
     *nt1 = e < n_tiles ? e : n_tiles;

@@ -183,6 +183,7 @@ int linear_impl(const void* a_dev, const void* w_dev, const void* bias_dev, cons
     rc = make_tmap_3d_f16(&tb, w_dev, K, N, 1, K, static_cast<uint64_t>(N) * K, gemm::BK, 160);
     if (rc) return rc;
     wk.plan(M, N, K, 1, 160, sms, 16, 1);
+    wk.n_fastest = 1;
     return gemm::launch<160, StoreEpi>(ta, tb, wk, epi, sms, stream);
   }
   const bool wide = (N % 256 == 0) || N >= 1024;
@@ -190,11 +191,13 @@ int linear_impl(const void* a_dev, const void* w_dev, const void* bias_dev, cons
     rc = make_tmap_3d_f16(&tb, w_dev, K, N, 1, K, static_cast<uint64_t>(N) * K, gemm::BK, 256);
     if (rc) return rc;
     wk.plan(M, N, K, 1, 256, sms, 16, 1);
+    wk.n_fastest = 1;
     return gemm::launch<256, StoreEpi>(ta, tb, wk, epi, sms, stream);
   }
   rc = make_tmap_3d_f16(&tb, w_dev, K, N, 1, K, static_cast<uint64_t>(N) * K, gemm::BK, 128);
   if (rc) return rc;
   wk.plan(M, N, K, 1, 128, sms, 16, 1);
+  wk.n_fastest = 1;
   return gemm::launch<128, StoreEpi>(ta, tb, wk, epi, sms, stream);
 }
 }  // namespace
@@ -232,5 +235,6 @@ extern "C" int vtm_linear_geglu_f16(const void* a_dev, const void* w_il_dev, con
   if (rc) return rc;
   gemm::Work wk;
   wk.plan(M, N, K, 1, 256, sms, 16, 1);
+  wk.n_fastest = 1;
   return gemm::launch<256, GegluEpi>(ta, tb, wk, epi, sms, stream);
 }
