@@ -28,7 +28,9 @@ One JSON line (rank 0):
 Multi-GPU (`--gpus N` under torchrun): local merging makes frame chunks independent (generate.py:216-219), so
 each rank denoises its own 16-frame chunk with replicated weights; nothing crosses GPUs in the data path
 ("scaling": "weak").  Timing = max over ranks of the CUDA-event time between two barriers.
-`--c4-global` (N > 1, opt-in) appends BASELINE config 4 with the global-token exchange (p2p and all-gather).
+For N > 1 the line also carries `c4_global`: BASELINE config 4 (SD2.1 768^2, one 8-frame chunk per GPU, global-token
+exchange as NCCL all-gather and fused into the merge gather over peer memory); a watchdog prints the line without it if the
+block does not return (`--no-c4-global` skips it).
 """
 from __future__ import annotations
 
@@ -440,9 +442,14 @@ def run_ours(args):
     events = dict(ops.STATS.events)
     ops.STATS.reset()
 
-    c4 = None
-    if world > 1 and args.c4_global:
-        c4 = c4_global_block(torch, dist, dev, rank, world, args.steps, timed)
+    line = {}
+
+    def emit():
+        """Print the one JSON line (rank 0).  Called exactly once: normally at the end; by the watchdog if the optional
+        config-4 block does not come back (a stuck collective cannot be cancelled, but it must not cost the headline)."""
+        if rank == 0 and line and not line.get("_printed"):
+            line["_printed"] = True
+            print(json.dumps({k: v for k, v in line.items() if k != "_printed"}), flush=True)
 
     if rank == 0:
         pk = peaks()
@@ -504,8 +511,6 @@ def run_ours(args):
             "roofline": roof,
             "rooflines": others,
         }
-        if c4 is not None:
-            out["c4_global"] = c4
         if world == 1 and not args.no_gpu_ref:
             vidtome_b200.remove_patch(net)
             out["comparators"] = comparators(torch, net, dev, args.steps, kind, cond)
@@ -523,7 +528,25 @@ def run_ours(args):
                 cb["numpy_oracle"] = {"value": round(1.0 / (5 * u1 + 5 * u2), 5), "unit": "steps/s",
                                       "sample": "numpy oracle, same two block calls (%.2f s, %.3f s)" % (u1, u2)}
             out["cpu_baseline"] = cb
-        print(json.dumps(out), flush=True)
+        line.update(out)
+    # BASELINE config 4 (global-token exchange) as a secondary block of the N > 1 line; guarded by a watchdog
+    if world > 1 and not args.no_c4_global:
+        def bail():
+            if rank == 0:
+                line["c4_global"] = {"error": "timed out after %d s; headline numbers above are unaffected" % args.c4_timeout}
+            emit()
+            os._exit(0)
+        wd = threading.Timer(args.c4_timeout, bail)
+        wd.daemon = True
+        wd.start()
+        try:
+            c4 = c4_global_block(torch, dist, dev, rank, world, args.steps, timed)
+        except Exception as exc:
+            c4 = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        wd.cancel()
+        if rank == 0:
+            line["c4_global"] = c4
+    emit()
     if world > 1:
         dist.destroy_process_group()
 
@@ -540,8 +563,10 @@ def main():
     ap.add_argument("--no-numpy", action="store_true", help="skip the numpy-oracle second CPU figure")
     ap.add_argument("--no-gpu-ref", action="store_true", help="skip the same-GPU comparators")
     ap.add_argument("--e2e-eager", action="store_true", help="end-to-end leg without CUDA-graph replay")
-    ap.add_argument("--c4-global", action="store_true",
-                    help="N > 1 only: append BASELINE config 4 with the global-token exchange (all-gather and fused p2p)")
+    ap.add_argument("--c4-global", action="store_true", help="(default for N > 1; kept for compatibility)")
+    ap.add_argument("--no-c4-global", action="store_true",
+                    help="N > 1: skip the secondary BASELINE config-4 block (global-token exchange: all-gather and fused p2p)")
+    ap.add_argument("--c4-timeout", type=int, default=240, help="watchdog for the config-4 block, seconds")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -45,3 +45,20 @@ def test_restatement_equals_reference_on_cpu(frames, monkeypatch):
         monkeypatch.setattr(torch, "randint", real_randint)
         monkeypatch.setattr(torch.Tensor, "argsort", real_argsort)
     assert torch.equal(outs[0], outs[1])
+
+
+def test_config1_plumbing_on_cpu():
+    """BASELINE config 1 as the reference defines it (device=cpu, 4 frames, 10 DDIM steps, local merge only: plumbing,
+    no GPU): the reference formulation (baseline/torch_reference_path.py, the CPU arm of bench.py) through the chunked
+    DDIM driver on the CPU in fp32.  The CUDA package itself has no CPU path by design."""
+    sys.path.insert(0, ROOT)
+    from baseline import torch_reference_path as R
+    from vidtome_b200.driver import ChunkedDenoiser
+    from vidtome_b200.skeleton import make_skeleton
+    net = make_skeleton("tiny", device="cpu", dtype=torch.float32, hot_path_only=False, seed=4)
+    R.apply_reference_path(net, 0.95, 2)
+    den = ChunkedDenoiser(net, n_timesteps=10, chunk_size=4, cond=torch.randn(2, 7, 768))
+    torch.manual_seed(0)
+    x = den.sample(torch.randn(4, 4, 16, 16))
+    assert x.shape == (4, 4, 16, 16) and torch.isfinite(x).all()
+    R.remove_reference_path(net)

@@ -302,7 +302,7 @@ def test_patched_block_matches_reference_block(name, monkeypatch):
     same_maps = np.array_equal(plan.pi.cpu().numpy().astype(np.int64), pi_o)
     print(f"{name}: arg-max ties flipped {nflip}, identical unmerge map: {same_maps}, max rel vs reference {rel.max():.2e}")
     if same_maps:
-        assert rel.max() <= 2e-3
+        assert rel.max() <= 1e-3          # north_star's tolerance, at MAX-norm (measured 8.6e-4 / 4.1e-4)
     else:
         assert rel.median() < 1e-3
     vidtome_b200.remove_patch(net)

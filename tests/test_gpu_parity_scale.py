@@ -344,3 +344,33 @@ def test_robust_block_fixture_max_norm(name, tol, monkeypatch):
     scale = ref.abs().max().item()
     print(f"{name}: max |err| / max |ref| = {err / scale:.2e}")
     assert err <= tol * scale
+
+
+# --------------------------------------------------------------------------- BASELINE config 1 (tea-pour) shape
+def test_config1_tea_pour_shape_ten_steps():
+    """BASELINE config 1 (configs/tea-pour.yaml: 4 frames, 10 DDIM steps, local merge only, ratio 0.95) on the SD1.5
+    skeleton through the chunked driver: level size and merged length of SURVEY App. B (12288 x 4096, r = 11673,
+    L = 4711 at ds1), ten steps stay finite, graph replay equals eager stepping."""
+    from types import SimpleNamespace
+    import vidtome_b200
+    from vidtome_b200 import patch
+    from vidtome_b200.driver import ChunkedDenoiser
+    from vidtome_b200.skeleton import make_skeleton
+    B, F, T, C = 2, 4, 4096, 320
+    g = torch.Generator(device="cuda").manual_seed(1)
+    base = torch.randn((B, 1, T, C), generator=g, device="cuda")
+    x = (base + 0.1 * torch.randn((B, F, T, C), generator=g, device="cuda")).half().reshape(B * F, T, C)
+    plan = patch.build_merge_plan(SimpleNamespace(generator=cuda_gen(), global_tokens=None), x,
+                                  _info(B, (64, 64), local_merge_ratio=0.95))
+    assert [(m.Ns, m.Nd, m.r) for m in plan.levels] == [(12288, 4096, 11673)]
+    assert plan.merged_tokens.shape[1] == 4711
+    outs = []
+    for graph in (False, True):
+        torch.manual_seed(11); torch.cuda.manual_seed(11)
+        net = make_skeleton("sd15", device="cuda", seed=3)
+        vidtome_b200.apply_patch(net, local_merge_ratio=0.95, batch_size=2)
+        den = ChunkedDenoiser(net, n_timesteps=10, chunk_size=4, cuda_graph=graph)
+        lat = torch.randn((4, 4, 64, 64), generator=torch.Generator(device="cuda").manual_seed(2), device="cuda", dtype=torch.float16)
+        outs.append(den.sample(lat))
+        assert torch.isfinite(outs[-1]).all()
+    assert torch.equal(outs[0], outs[1])
