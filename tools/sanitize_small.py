@@ -32,5 +32,39 @@ for variant in ("cta", "pair"):
     plan = patch.build_merge_plan(mod, x, info)
     out = plan.unmerge_add(plan.merged_tokens, x)
     assert torch.isfinite(out).all()
+# ---- r02 additions
+# fused LayerNorm in K0 / KC (packed fp32 rows, gamma / beta in shared memory), ragged channel counts
+for C in (320, 640, 1280, 136):
+    xx = torch.randn((2, 4 * 40, C), generator=g, device="cuda").half()
+    ln = (torch.ones(C, device="cuda").half(), torch.zeros(C, device="cuda").half(), 1e-5)
+    from vidtome_b200._lib import VtmSplit
+    a_, b_ = ops.normalize_split(xx, None, VtmSplit.local(160, 0, 4, 4, 1), ln=ln)
+    y_ = ops.layer_norm(xx.view(-1, C), ln)
+    assert torch.isfinite(a_).all() and torch.isfinite(y_).all()
+# merge modes (exact reduction with 64-bit atomics)
+from vidtome_b200 import merge
+xm = torch.randn((2, 4 * 48, 128), generator=g, device="cuda").half()
+m_, u_, _ = merge.bipartite_soft_matching_randframe(xm, 4, 0.9, 0, torch.Generator(device="cuda").manual_seed(2))
+for mode in ("mean", "sum", "amax", "amin"):
+    assert torch.isfinite(m_(xm, mode=mode)).all()
+# feed-forward GEMMs: GEGLU epilogue, residual epilogue with 160-wide tiles (N = 320), ragged M
+for (M, K, inner) in [(333, 320, 1280), (1000, 640, 2560)]:
+    a = torch.randn((M, K), generator=g, device="cuda").half()
+    w = (torch.randn((2 * inner, K), generator=g, device="cuda") / K ** 0.5).half()
+    bb = torch.randn((2 * inner,), generator=g, device="cuda").half()
+    wi, bi = ops.interleave_geglu(w, bb)
+    uu = ops.linear_geglu(a, wi, bi)
+    w2 = (torch.randn((K, inner), generator=g, device="cuda") / inner ** 0.5).half()
+    out = ops.linear_residual(uu, w2, torch.zeros(K, device="cuda").half(), a)
+    assert torch.isfinite(out).all()
+# cross-attention (Lq != Lk, one ragged key tile) and PnP's shared q / k
+xq = torch.randn((3, 333, 320), generator=g, device="cuda").half()
+ctx = torch.randn((3, 77, 768), generator=g, device="cuda").half()
+wq = (torch.randn((320, 320), generator=g, device="cuda") / 18).half()
+wkv = (torch.randn((640, 768), generator=g, device="cuda") / 28).half()
+y = ops.cross_attention(xq, ctx, wq, wkv, wq, torch.zeros(320, device="cuda").half(), 8, 40 ** -0.5, resid=xq)
+assert torch.isfinite(y).all()
+y = ops.attention(xq, torch.cat([wq, wq, wq], 0).contiguous(), wq, None, 8, 40 ** -0.5, shared_qk=True)
+assert torch.isfinite(y).all()
 torch.cuda.synchronize()
-print("sanitize_small: ok")
+print("sanitize_small: ok (VTM_FA_GROUPS=%s)" % os.environ.get("VTM_FA_GROUPS", "0"))
