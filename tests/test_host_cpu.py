@@ -382,3 +382,34 @@ def test_pnp_torch_forward_equals_reference_fixture_on_cpu():
     assert patch._plain_attention_module(attn)
     attn.forward = lambda *a, **k: None
     assert not patch._plain_attention_module(attn)
+
+
+# --------------------------------------------------------------------------- callers
+def test_get_chunks_matches_reference_for_every_order_mode():
+    """driver.ChunkedDenoiser.get_chunks against `Generator.get_chunks` itself (generate.py:172-203; its source is
+    extracted from the reference file and run by tests/make_golden_r02.py --callers): same numpy / torch RNG seeds ->
+    the same chunk lists for seq, rand, mix and mix-# orders, with and without global merging, short first chunks."""
+    import json
+    from vidtome_b200.driver import ChunkedDenoiser
+    cases = json.load(open(os.path.join(ROOT, "tests", "golden", "callers_get_chunks.json")))
+    assert len(cases) >= 9
+    for c in cases:
+        den = ChunkedDenoiser(_skeleton(), chunk_size=c["chunk_size"], merge_global=c["merge_global"],
+                              chunk_ord=c["chunk_ord"], randomize_chunks=True)
+        np.random.seed(c["seed"])
+        torch.manual_seed(c["seed"])
+        got = [[int(v) for v in ch] for ch in den.get_chunks(c["flen"])]
+        assert got == c["chunks"], c
+
+
+def test_ddim_update_matches_reference_pred_next_x():
+    """driver.pred_next_x against `Generator.pred_next_x` (generate.py:281-311, extracted the same way) on SD's
+    scaled-linear schedule: first, middle and last steps."""
+    from vidtome_b200.driver import ChunkedDenoiser
+    g = np.load(os.path.join(ROOT, "tests", "golden", "callers_pred_next_x.npz"))
+    den = ChunkedDenoiser(_skeleton(), n_timesteps=50)
+    x, eps = torch.from_numpy(g["x"]), torch.from_numpy(g["eps"])
+    for i in (0, 1, 25, 48, 49):
+        want = torch.from_numpy(g[f"i{i}"]).float()
+        got = den.pred_next_x(x, eps, i).float()
+        assert (got - want).abs().max().item() <= 2e-3 * want.abs().max().item() + 1e-3, i

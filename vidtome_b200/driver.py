@@ -36,7 +36,7 @@ class ChunkedDenoiser:
 
     def __init__(self, unet: torch.nn.Module, n_timesteps: int = 50, chunk_size: int = 16,
                  guidance_scale: float = 7.5, merge_global: bool = False, chunk_ord: str = "seq",
-                 perm_div: int = 4, randomize_chunks: bool = False, cond: Optional[torch.Tensor] = None,
+                 perm_div: float = 3.0, randomize_chunks: bool = False, cond: Optional[torch.Tensor] = None,
                  cuda_graph: bool = False, graph_warmup: int = 2, shard: bool = False):
         """`cuda_graph=True`: after `graph_warmup` eager steps, the noise prediction of a whole step (every chunk:
         CFG batch, UNet forward with the merge path, guidance combine) is captured once into a CUDA graph and
@@ -59,6 +59,10 @@ class ChunkedDenoiser:
         self.chunk_size = chunk_size
         self.guidance_scale = guidance_scale
         self.merge_global = merge_global
+        # generate.py:86-89: "mix-#" means a partial permutation of len/# chunks ("mix" alone: # = 3)
+        if "mix" in chunk_ord:
+            perm_div = float(chunk_ord.split("-")[-1]) if "-" in chunk_ord else (perm_div if perm_div else 3.0)
+            chunk_ord = "mix"
         self.chunk_ord, self.perm_div = chunk_ord, perm_div
         self.randomize_chunks = randomize_chunks
         self.cond = cond                      # [2, 77, D] (uncond, cond) text embeddings, may be None
@@ -79,7 +83,7 @@ class ChunkedDenoiser:
             return chunks
         if self.chunk_ord == "rand":
             order = torch.randperm(len(chunks)).tolist()
-        elif self.chunk_ord.startswith("mix"):
+        elif self.chunk_ord == "mix":
             randord = torch.randperm(len(chunks)).tolist()
             rand_len = int(len(randord) / self.perm_div)
             seqord = sorted(randord[rand_len:])
