@@ -220,16 +220,32 @@ __device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int tar
 }
 
 // exclusive prefix of hist[bucket][tile] in (bucket, tile) order for ONE (bucket, tile) pair per thread:
-// thread t (t < 256) gets the base of bucket t for this CTA's tile.
+// thread t (t < 256) gets the base of bucket t for this CTA's tile.  All 1024 threads share the column sums: thread
+// (bucket = t % 256, quarter = t / 256) adds a quarter of the tiles with independent loads in flight (the first version
+// walked all tiles from one thread per bucket: a chain of ~50 dependent L2 latencies per pass, the bulk of the kernel).
 __device__ __forceinline__ uint32_t bucket_base(const uint32_t* __restrict__ h /* [256][tiles] */, int tiles,
-                                                int my_tile, uint32_t* s_scan /* [256] */) {
+                                                int my_tile, uint32_t* s_scan /* [256] */, uint32_t (*s_part)[256] /* [8][256] */) {
+  {
+    const int bucket = threadIdx.x & 255, quarter = threadIdx.x >> 8;
+    const int t0 = quarter * tiles / 4, t1 = (quarter + 1) * tiles / 4;
+    const uint32_t* row = h + static_cast<size_t>(bucket) * tiles;
+    uint32_t tot = 0, bef = 0;
+#pragma unroll 4
+    for (int t = t0; t < t1; ++t) {
+      const uint32_t c = __ldcg(row + t);
+      tot += c;
+      bef += t < my_tile ? c : 0u;
+    }
+    s_part[quarter][bucket] = tot;
+    s_part[4 + quarter][bucket] = bef;
+  }
+  __syncthreads();
   uint32_t total = 0, before = 0;
   if (threadIdx.x < 256) {
-    const uint32_t* row = h + static_cast<size_t>(threadIdx.x) * tiles;
-    for (int t = 0; t < tiles; ++t) {
-      const uint32_t c = __ldcg(row + t);
-      if (t < my_tile) before += c;
-      total += c;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      total += s_part[q][threadIdx.x];
+      before += s_part[4 + q][threadIdx.x];
     }
     s_scan[threadIdx.x] = total;
   }
@@ -265,6 +281,7 @@ radix_sort_fused_kernel(const unsigned long long* __restrict__ keys, int Ns, int
   __shared__ uint32_t s_tot[256];
   __shared__ uint32_t s_base[256];
   __shared__ uint32_t s_scan[256];
+  __shared__ uint32_t s_part[8][256];
   const int b = blockIdx.y, tile = blockIdx.x;
   const unsigned int nblk = gridDim.x * gridDim.y;
   const size_t row0 = static_cast<size_t>(b) * Ns;
@@ -277,7 +294,7 @@ radix_sort_fused_kernel(const unsigned long long* __restrict__ keys, int Ns, int
   uint32_t* h0 = hist0 + static_cast<size_t>(b) * 256 * tiles;
   if (threadIdx.x < 256) h0[static_cast<size_t>(threadIdx.x) * tiles + tile] = s_tot[threadIdx.x];
   grid_barrier(barrier_ctr, nblk);
-  uint32_t base = bucket_base(h0, tiles, tile, s_scan);
+  uint32_t base = bucket_base(h0, tiles, tile, s_scan, s_part);
   if (threadIdx.x < 256) s_base[threadIdx.x] = base;
   __syncthreads();
   if (valid) {
@@ -297,7 +314,7 @@ radix_sort_fused_kernel(const unsigned long long* __restrict__ keys, int Ns, int
   uint32_t* h1 = hist1 + static_cast<size_t>(b) * 256 * tiles;
   if (threadIdx.x < 256) h1[static_cast<size_t>(threadIdx.x) * tiles + tile] = s_tot[threadIdx.x];
   grid_barrier(barrier_ctr, 3 * nblk);
-  base = bucket_base(h1, tiles, tile, s_scan);
+  base = bucket_base(h1, tiles, tile, s_scan, s_part);
   if (threadIdx.x < 256) s_base[threadIdx.x] = base;
   __syncthreads();
   if (valid) {
@@ -353,12 +370,19 @@ extern "C" int vtm_topr_sort(const uint64_t* keys_dev, int32_t Bp, int32_t Ns, i
   dim3 grid(tiles, Bp);
   // single cooperative launch when every CTA can be resident at once
   {
+    // device facts: looked up once per device ordinal (immutable afterwards)
+    static int t_sms[64], t_per_sm[64], t_coop[64];
     int dev = 0, sms = 0, per_sm = 0, coop = 0;
     int rc = cuda_rc(cudaGetDevice(&dev));
     if (rc) return rc;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, radix_sort_fused_kernel, TILE, 0);
+    if (dev >= 0 && dev < 64 && t_sms[dev] > 0) {
+      sms = t_sms[dev]; per_sm = t_per_sm[dev]; coop = t_coop[dev];
+    } else {
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, radix_sort_fused_kernel, TILE, 0);
+      if (dev >= 0 && dev < 64 && sms > 0) { t_per_sm[dev] = per_sm; t_coop[dev] = coop; t_sms[dev] = sms; }
+    }
     if (coop && static_cast<long long>(tiles) * Bp <= static_cast<long long>(sms) * per_sm) {
       rc = cuda_rc(cudaMemsetAsync(ws.barrier, 0, sizeof(unsigned int), st));
       if (rc) return rc;
