@@ -387,9 +387,14 @@ extern "C" int vtm_topr_sort(const uint64_t* keys_dev, int32_t Bp, int32_t Ns, i
       rc = cuda_rc(cudaMemsetAsync(ws.barrier, 0, sizeof(unsigned int), st));
       if (rc) return rc;
       int ns = Ns, tl = tiles;
-      void* args[] = {(void*)&keys, (void*)&ns, (void*)&tl, (void*)&ws.hist, (void*)&ws.hist1, (void*)&ws.k_tmp,
-                      (void*)&ws.id_tmp, (void*)&edge_dev, (void*)&rank_dev, (void*)&ws.barrier};
-      return cuda_rc(cudaLaunchCooperativeKernel((const void*)radix_sort_fused_kernel, grid, dim3(TILE), args, 0, st));
+      // A plain launch: every CTA of the grid fits on the device at once (checked above), and kernels ahead of this one
+      // — earlier in the stream, or on other streams — finish without depending on it, so all CTAs become resident
+      // and the spin barriers cannot deadlock.  The cooperative launch API adds host-side validation per call and a
+      // heavier launch path; measured r02.
+      (void)ns; (void)tl;
+      radix_sort_fused_kernel<<<grid, TILE, 0, st>>>(keys, Ns, tiles, ws.hist, ws.hist1, ws.k_tmp, ws.id_tmp, edge_dev,
+                                                    rank_dev, ws.barrier);
+      return launch_rc();
     }
   }
   radix_hist_kernel<0><<<grid, TILE, 0, st>>>(keys, nullptr, Ns, tiles, ws.hist);
