@@ -45,6 +45,8 @@ struct HeadSplitEpi {
   __half* qkvh;
   int M, C, H, d, L, DP, nb; // M = nb*L rows, C = H*d
   int which0, n_proj;        // this GEMM produces projections which0 .. which0 + n_proj - 1 of (q, k, v); N = n_proj * C
+  float qscale;              // q is written as fp16(q * qscale) (1 = plain; softmax scale * log2 e for the embedded reference)
+  int kones;                 // also write 1.0 into padding column d of K (embedded reference, flash_attn_kernel EMB)
   long long which_stride;    // B*H*L*DP
   int row0;                  // first of the warp's 32 rows
   uint32_t scratch;
@@ -68,7 +70,10 @@ struct HeadSplitEpi {
       tmem_ld_wait();
       uint32_t pk[32];
 #pragma unroll
-      for (int e = 0; e < 32; ++e) pk[e] = pack_f16x2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
+      for (int e = 0; e < 32; ++e) {
+        const float sc = (which0 == 0 && col0 + cb + 2 * e < C) ? qscale : 1.f;     // q columns only (C is even)
+        pk[e] = pack_f16x2(__uint_as_float(r[2 * e]) * sc, __uint_as_float(r[2 * e + 1]) * sc);
+      }
       // this lane's 8 columns in the store phase: the same for all of its rows
       const int n = col0 + cb + (threadIdx.x & 7) * 8;       // groups of 8 columns never straddle a head (d % 8 == 0)
       const bool n_ok = n < n_proj * C && (threadIdx.x & 7) * 8 < ncols - cb;   // BN = 160: 16-column second chunk
@@ -88,7 +93,8 @@ struct HeadSplitEpi {
             // padding columns: zeros — except column d of V, which holds 1.0 so that the P V MMA also produces
             // the softmax denominator (flash_attn_kernel, ONES)
             const uint4 z = make_uint4(0, 0, 0, 0);
-            *reinterpret_cast<uint4*>(dst + 8) = which + which0 == 2 ? make_uint4(0x00003C00u, 0, 0, 0) : z;
+            const bool one = which + which0 == 2 || (kones && which + which0 == 1);
+            *reinterpret_cast<uint4*>(dst + 8) = one ? make_uint4(0x00003C00u, 0, 0, 0) : z;
             for (int pe = d + 8; pe < DP; pe += 8) *reinterpret_cast<uint4*>(dst + 8 + (pe - d)) = z;
           }
         }
@@ -104,14 +110,14 @@ struct HeadSplitEpi {
 // x [nb * L, K] -> projections which0 .. which0 + n_proj - 1 of (q, k, v), head-major padded, at `out`
 // ([n_proj][nb][H][L][DP]); w [n_proj * C, K].
 int launch_head_proj(const void* x, const void* w, __half* out, int nb, int L, int K, int C, int H, int DP, int which0,
-                     int n_proj, cudaStream_t stream) {
+                     int n_proj, float qscale, int kones, cudaStream_t stream) {
   int sms = 0;
   int rc = gemm::device_sms(&sms);
   if (rc) return rc;
   const int M = nb * L, N = n_proj * C;
   HeadSplitEpi epi;
   epi.qkvh = out; epi.M = M; epi.C = C; epi.H = H; epi.d = C / H; epi.L = L; epi.DP = DP;
-  epi.which0 = which0; epi.n_proj = n_proj;
+  epi.which0 = which0; epi.n_proj = n_proj; epi.qscale = qscale; epi.kones = kones;
   epi.which_stride = static_cast<long long>(nb) * H * L * DP; epi.row0 = 0; epi.scratch = 0; epi.b0 = 0; epi.l0 = 0; epi.nb = nb;
   CUtensorMap ta, tb;
   rc = make_tmap_3d_f16(&ta, x, K, M, 1, K, static_cast<uint64_t>(M) * K, gemm::BK, gemm::BM);
@@ -131,9 +137,9 @@ int launch_head_proj(const void* x, const void* w, __half* out, int nb, int L, i
   return gemm::launch<128, HeadSplitEpi>(ta, tb, wk, epi, sms, stream);
 }
 
-int launch_qkv_heads(const void* x, const void* w_qkv, __half* qkvh, int B, int L, int C, int H, int DP,
-                     cudaStream_t stream) {
-  return launch_head_proj(x, w_qkv, qkvh, B, L, C, C, H, DP, 0, 3, stream);
+int launch_qkv_heads(const void* x, const void* w_qkv, __half* qkvh, int B, int L, int C, int H, int DP, float qscale,
+                     int kones, cudaStream_t stream) {
+  return launch_head_proj(x, w_qkv, qkvh, B, L, C, C, H, DP, 0, 3, qscale, kones, stream);
 }
 
 #ifndef VTM_FA2_STAGGER_NS
@@ -215,13 +221,16 @@ __device__ __forceinline__ float fa_row_max(const uint32_t (&r)[NCH][32], int n_
 #ifndef VTM_FA_POLY_DEN
 #define VTM_FA_POLY_DEN 16
 #endif
-template <bool TAIL, bool SUM>
+// MODE 0: x = s * c - mc (scores in raw units);  MODE 1: x = s (the scores already ARE the exponents: scale folded into
+// q and the reference embedded in the QK product, see the EMB path of flash_attn_kernel);  MODE 2: x = s - mc.
+template <bool TAIL, bool SUM, int MODE = 0>
 __device__ __forceinline__ void fa_exp32(const uint32_t (&r)[32], uint32_t (&pk)[16], float c, float mc, int col0,
                                          int n_valid, float& sum0, float& sum1) {
   const uint64_t c2 = f32x2_pack(c, c), nmc2 = f32x2_pack(-mc, -mc);
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    const uint64_t x2 = f32x2_fma(f32x2_pack(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), c2, nmc2);
+    const uint64_t s2 = f32x2_pack(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+    const uint64_t x2 = MODE == 0 ? f32x2_fma(s2, c2, nmc2) : (MODE == 1 ? s2 : f32x2_add(s2, nmc2));
     float p0, p1;
     // pair i goes to the polynomial when the running count floor((i+1) NUM / DEN) steps: an even spread
     if (((i + 1) * VTM_FA_POLY_NUM) / VTM_FA_POLY_DEN != (i * VTM_FA_POLY_NUM) / VTM_FA_POLY_DEN) {
@@ -249,7 +258,14 @@ __device__ __forceinline__ void fa_exp32(const uint32_t (&r)[32], uint32_t (&pk)
 // follows every rescale of O automatically and is the sum of exactly the fp16 P values the numerator uses; the
 // softmax warps drop one FADD per score.  Measured effect on time: -0.6 % at L=10241, none at L=21300 (same-box
 // A/B against -DVTM_FA_NO_ONES) — the row sums were not what limits the softmax warps.
-template <int KSTEPS, bool ONES>
+// EMB (requires ONES, i.e. head_dim % 16 == 8 and a spare column in the padded rows): the softmax scale * log2 e is folded
+// into q by the projection epilogue, column d of every K row holds 1.0 and column d of a Q row holds MINUS the reference
+// maximum of that query row, so that the tensor core delivers s' = exponent - reference directly: the softmax warps issue
+// MUFU.EX2 on the accumulators as loaded, without the FFMA (and the dependency level) per score.  A thread owns its row's
+// reference: it rewrites the 2-byte column in shared memory (swizzled address) when the reference moves — after the one
+// QK MMA that may still be reading the tile has completed (s_full of the next tile) — and keeps track of which reference
+// each tile's scores embed (QK runs one tile ahead, so a new reference takes effect two tiles later).
+template <int KSTEPS, bool ONES, bool EMB = false>
 __global__ void __launch_bounds__(FA_THREADS, FaCfg<KSTEPS>::MIN_CTAS)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                   const __grid_constant__ CUtensorMap tm_v, const FaParams p) {
@@ -414,6 +430,106 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
       if (slot & 1u) __nanosleep(VTM_FA2_STAGGER_NS);
     }
 #endif
+    if constexpr (EMB) {
+      static_assert(ONES, "the embedded reference uses the spare column of head_dim % 16 == 8");
+      const int rit = quad * 32 + lane;                                  // row in the Q tile
+      const int dcol = p.d & 63, datom = p.d >> 6;                       // column d inside its 64-wide block
+      const uint32_t q_ref_addr = sQ + datom * (BQ * 128) + rit * 128 + ((((2 * dcol) >> 4) ^ (rit & 7)) << 4) + ((2 * dcol) & 15);
+      float m_O = -INFINITY;           // reference of O and of every P accumulated so far (log2 units, fp16-exact)
+      float e_tile0 = 0.f, e_tile1 = 0.f;   // reference embedded in the scores of tile j (j even / odd)
+      float e_q = 0.f;                 // reference currently in shared memory (embedded from tile j + 2 on)
+      float dummy0 = 0.f, dummy1 = 0.f;
+      for (int j = 0; j < nkv; ++j) {
+        mbar_wait(s_full(j & 1), (j >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t s_addr = tmem_base + lane_field + (j & 1) * BKV;
+        const int n_valid = p.L - (j_lo + j) * BKV;
+        const bool tail = n_valid < BKV;
+        constexpr int NCH = BKV / 32;
+        uint32_t r[NCH][32];
+        const float e = (j & 1) ? e_tile1 : e_tile0;
+        float mx;
+        bool slow;
+        if (j == 0 || tail) {
+#pragma unroll
+          for (int ch = 0; ch < NCH; ++ch) tmem_ld_32x32b_x32(s_addr + 32 * ch, r[ch]);
+          tmem_ld_wait();
+          mx = tail ? fa_row_max<NCH, true>(r, n_valid) : fa_row_max<NCH, false>(r, n_valid);
+          slow = true;
+        } else {
+          // speculative: the scores are the exponents as long as this tile embeds O's reference and stays below 2^8
+          float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+          tmem_ld_32x32b_x32(s_addr, r[0]);
+#pragma unroll
+          for (int ch = 0; ch < NCH; ++ch) {
+            tmem_ld_wait();
+            if (ch + 1 < NCH) tmem_ld_32x32b_x32(s_addr + 32 * (ch + 1), r[ch + 1]);
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              m0 = fmax3(m0, __uint_as_float(r[ch][i]), __uint_as_float(r[ch][i + 1]));
+              m1 = fmax3(m1, __uint_as_float(r[ch][i + 2]), __uint_as_float(r[ch][i + 3]));
+              m2 = fmax3(m2, __uint_as_float(r[ch][i + 4]), __uint_as_float(r[ch][i + 5]));
+              m3 = fmax3(m3, __uint_as_float(r[ch][i + 6]), __uint_as_float(r[ch][i + 7]));
+            }
+            uint32_t pk[16];
+            fa_exp32<false, false, 1>(r[ch], pk, 0.f, 0.f, 32 * ch, n_valid, dummy0, dummy1);
+            tmem_st_32x32b_x16(s_addr + 16 * ch, pk);
+          }
+          mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+          slow = __any_sync(0xffffffffu, !(e == m_O && mx <= RESCALE_LOG2));
+        }
+        float alpha = 1.f;
+        if (slow) {
+          // settle the reference for this tile: keep O's unless the row maximum exceeds it by more than 2^8, then move
+          // it to the maximum (rounded UP to fp16 so that it can be embedded exactly)
+          const float abs_max = e + mx;
+          float r_new = m_O;
+          if (!(abs_max - m_O <= RESCALE_LOG2)) r_new = __half2float(__float2half_ru(abs_max));   // also the first tile (m_O = -inf)
+          if (r_new != m_O) {
+            alpha = ex2_approx(m_O - r_new);       // 0 on the first tile
+            m_O = r_new;
+          }
+          const float delta = m_O - e;              // exponent = s' - delta
+#pragma unroll
+          for (int ch = 0; ch < NCH; ++ch) {
+            uint32_t pk[16];
+            if (tail) fa_exp32<true, false, 2>(r[ch], pk, 0.f, delta, 32 * ch, n_valid, dummy0, dummy1);
+            else fa_exp32<false, false, 2>(r[ch], pk, 0.f, delta, 32 * ch, n_valid, dummy0, dummy1);
+            tmem_st_32x32b_x16(s_addr + 16 * ch, pk);
+          }
+        }
+        if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+          mbar_wait(o_ready((j - 1) & 1), ((j - 1) >> 1) & 1u);
+          tc_fence_after();
+#pragma unroll
+          for (int cb = 0; cb < C::DV_N; cb += 16) {
+            uint32_t ro[16];
+            tmem_ld_32x32b_x16(tmem_o + lane_field + cb, ro);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
+            tmem_st_32x32b_x16(tmem_o + lane_field + cb, ro);
+          }
+        }
+        // publish O's reference for the tiles whose QK has not been issued yet (j + 2 onwards)
+        if (j + 2 < nkv && __any_sync(0xffffffffu, e_q != m_O)) {
+          // QK of tile j + 1 (issued with the old column) may still be reading this Q tile: wait for its commit
+          mbar_wait(s_full((j + 1) & 1), ((j + 1) >> 1) & 1u);
+          if (e_q != m_O) {
+            const unsigned short neg = __half_as_ushort(__float2half_rn(-m_O));
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(q_ref_addr), "h"(neg) : "memory");
+            e_q = m_O;
+          }
+          fence_proxy_async_smem();    // generic-proxy store -> visible to the tensor core's (async proxy) operand reads
+        }
+        if (j & 1) e_tile1 = e_q; else e_tile0 = e_q;     // what tile j + 2 will embed
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full(j & 1));
+      }
+      m_ref = m_O;      // log2 units already (see the partial-result store below)
+    } else
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(s_full(j & 1), (j >> 1) & 1u);
       tc_fence_after();
@@ -535,7 +651,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     } else {
       // ---- split tile: un-normalised O, reference max and denominator of this key range
       const size_t prow = (static_cast<size_t>(tile - p.n_full) * nparts + part) * BQ + quad * 32 + lane;
-      p.part_ml[prow] = make_float2(m_ref * c, l_run);
+      p.part_ml[prow] = make_float2(EMB ? m_ref : m_ref * c, l_run);
       float* po = p.part_o + prow * C::DV_N;
 #pragma unroll
       for (int cb = 0; cb < C::DV_N; cb += 16) {
@@ -629,7 +745,7 @@ int fa_forced_splits() {
 
 template <int KSTEPS, bool ONES>
 int launch_fa_impl(const void* qh, const void* kh, const void* vh, __half* o, void* part_ws, int B, int Lq, int L, int C,
-                   int H, int d, float scale, int qk_shared, cudaStream_t stream) {
+                   int H, int d, float scale, int qk_shared, int emb, cudaStream_t stream) {
   using Cf = FaCfg<KSTEPS>;
   using Cg = FaGCfg<KSTEPS>;
   const bool groups = fa_use_groups();
@@ -659,6 +775,11 @@ int launch_fa_impl(const void* qh, const void* kh, const void* vh, __half* o, vo
     rc = cuda_rc(cudaFuncSetAttribute(flash_attn_groups_kernel<KSTEPS, ONES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(Cg::SMEM_BYTES)));
     if (rc) return rc;
+    if (ONES) {
+      rc = cuda_rc(cudaFuncSetAttribute(flash_attn_kernel<KSTEPS, ONES, ONES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(Cf::SMEM_BYTES)));
+      if (rc) return rc;
+    }
     rc = cuda_rc(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, flash_attn_kernel<KSTEPS, ONES>, FA_THREADS,
                                                                Cf::SMEM_BYTES));
     if (rc) return rc;
@@ -704,6 +825,8 @@ int launch_fa_impl(const void* qh, const void* kh, const void* vh, __half* o, vo
   const long long units = p.n_full + (tiles - p.n_full) * splits;
   if (groups)
     flash_attn_groups_kernel<KSTEPS, ONES><<<static_cast<unsigned>(units), Cg::THREADS, Cg::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  else if (ONES && emb)
+    flash_attn_kernel<KSTEPS, ONES, ONES><<<static_cast<unsigned>(units), FA_THREADS, Cf::SMEM_BYTES, stream>>>(tq, tk, tv, p);
   else
     flash_attn_kernel<KSTEPS, ONES><<<static_cast<unsigned>(units), FA_THREADS, Cf::SMEM_BYTES, stream>>>(tq, tk, tv, p);
   rc = launch_rc();
@@ -715,22 +838,36 @@ int launch_fa_impl(const void* qh, const void* kh, const void* vh, __half* o, vo
 
 template <int KSTEPS>
 int launch_fa(const void* qh, const void* kh, const void* vh, __half* o, void* part_ws, int B, int Lq, int L, int C, int H,
-              int d, float scale, int qk_shared, cudaStream_t stream) {
+              int d, float scale, int qk_shared, int emb, cudaStream_t stream) {
 #if !defined(VTM_FA_NO_ONES)   // A/B switch: keep the denominator in the softmax warps
   if (d % 16 == 8)
-    return launch_fa_impl<KSTEPS, true>(qh, kh, vh, o, part_ws, B, Lq, L, C, H, d, scale, qk_shared, stream);
+    return launch_fa_impl<KSTEPS, true>(qh, kh, vh, o, part_ws, B, Lq, L, C, H, d, scale, qk_shared, emb, stream);
 #endif
-  return launch_fa_impl<KSTEPS, false>(qh, kh, vh, o, part_ws, B, Lq, L, C, H, d, scale, qk_shared, stream);
+  return launch_fa_impl<KSTEPS, false>(qh, kh, vh, o, part_ws, B, Lq, L, C, H, d, scale, qk_shared, 0, stream);
+}
+
+// The embedded-reference path (flash_attn_kernel EMB) is used when the head dimension leaves a spare column
+// (head_dim % 16 == 8: the SD1.5 full-resolution blocks) and the 2-CTAs-per-SM kernel runs; VTM_FA_EMBED=0 switches
+// it off (A/B measurements).  Read once per process.
+bool fa_use_embed(int d) {
+  static const int v = [] {
+    const char* e = getenv("VTM_FA_EMBED");
+    return (e && e[0] == '0') ? 0 : 1;
+  }();
+#if defined(VTM_FA_NO_ONES)
+  return false;
+#endif
+  return v != 0 && d % 16 == 8 && !fa_use_groups();
 }
 
 int launch_fa_any(const void* qh, const void* kh, const void* vh, __half* o, void* part_ws, int B, int Lq, int L, int C,
-                  int H, int d, float scale, int qk_shared, cudaStream_t stream) {
+                  int H, int d, float scale, int qk_shared, int emb, cudaStream_t stream) {
   switch ((d + 15) / 16) {
-    case 1: case 2: case 3: return launch_fa<3>(qh, kh, vh, o, part_ws, B, Lq, L, C, H, d, scale, qk_shared, stream);
-    case 4: return launch_fa<4>(qh, kh, vh, o, part_ws, B, Lq, L, C, H, d, scale, qk_shared, stream);
-    case 5: return launch_fa<5>(qh, kh, vh, o, part_ws, B, Lq, L, C, H, d, scale, qk_shared, stream);
-    case 6: return launch_fa<6>(qh, kh, vh, o, part_ws, B, Lq, L, C, H, d, scale, qk_shared, stream);
-    default: return launch_fa<8>(qh, kh, vh, o, part_ws, B, Lq, L, C, H, d, scale, qk_shared, stream);
+    case 1: case 2: case 3: return launch_fa<3>(qh, kh, vh, o, part_ws, B, Lq, L, C, H, d, scale, qk_shared, emb, stream);
+    case 4: return launch_fa<4>(qh, kh, vh, o, part_ws, B, Lq, L, C, H, d, scale, qk_shared, emb, stream);
+    case 5: return launch_fa<5>(qh, kh, vh, o, part_ws, B, Lq, L, C, H, d, scale, qk_shared, emb, stream);
+    case 6: return launch_fa<6>(qh, kh, vh, o, part_ws, B, Lq, L, C, H, d, scale, qk_shared, emb, stream);
+    default: return launch_fa<8>(qh, kh, vh, o, part_ws, B, Lq, L, C, H, d, scale, qk_shared, emb, stream);
   }
 }
 
@@ -764,11 +901,12 @@ extern "C" int vtm_attention_ex(const void* x_dev, const void* w_qkv_dev, const 
   const int M = B * L;
   void* part_ws = reinterpret_cast<void*>(
       (reinterpret_cast<uintptr_t>(o + static_cast<size_t>(M) * C) + 255u) & ~static_cast<uintptr_t>(255u));
-  int rc = launch_qkv_heads(x_dev, w_qkv_dev, qkv, B, L, C, heads, DP, stream);
+  const int emb = fa_use_embed(d) ? 1 : 0;
+  int rc = launch_qkv_heads(x_dev, w_qkv_dev, qkv, B, L, C, heads, DP, emb ? scale * 1.4426950408889634f : 1.f, emb, stream);
   if (rc) return rc;
   const __half* kh = qkv + static_cast<size_t>(B) * heads * L * DP;
   const __half* vh = kh + static_cast<size_t>(B) * heads * L * DP;
-  rc = launch_fa_any(qkv, kh, vh, o, part_ws, B, L, L, C, heads, d, scale, flags & 1, stream);
+  rc = launch_fa_any(qkv, kh, vh, o, part_ws, B, L, L, C, heads, d, scale, flags & 1, emb, stream);
   if (rc) return rc;
   return vtm_linear_f16(o, w_o_dev, b_o_dev, M, C, C, y_dev, C, stream_);
 }
@@ -809,11 +947,12 @@ extern "C" int vtm_cross_attention(const void* x_dev, const void* ctx_dev, const
   __half* o = vh + static_cast<size_t>(B) * heads * Lk * DP;
   void* part_ws = reinterpret_cast<void*>(
       (reinterpret_cast<uintptr_t>(o + static_cast<size_t>(B) * Lq * C) + 255u) & ~static_cast<uintptr_t>(255u));
-  int rc = launch_head_proj(x_dev, w_q_dev, qh, B, Lq, C, C, heads, DP, 0, 1, stream);
+  const int emb = fa_use_embed(d) ? 1 : 0;
+  int rc = launch_head_proj(x_dev, w_q_dev, qh, B, Lq, C, C, heads, DP, 0, 1, emb ? scale * 1.4426950408889634f : 1.f, 0, stream);
   if (rc) return rc;
-  rc = launch_head_proj(ctx_dev, w_kv_dev, kh, B, Lk, Cctx, C, heads, DP, 1, 2, stream);
+  rc = launch_head_proj(ctx_dev, w_kv_dev, kh, B, Lk, Cctx, C, heads, DP, 1, 2, 1.f, emb, stream);
   if (rc) return rc;
-  rc = launch_fa_any(qh, kh, vh, o, part_ws, B, Lq, Lk, C, heads, d, scale, 0, stream);
+  rc = launch_fa_any(qh, kh, vh, o, part_ws, B, Lq, Lk, C, heads, d, scale, 0, emb, stream);
   if (rc) return rc;
   const int M = B * Lq;
   if (resid_dev) return vtm_linear_residual_f16(o, w_o_dev, b_o_dev, resid_dev, C, M, C, C, y_dev, C, stream_);
