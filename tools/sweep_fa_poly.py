@@ -68,8 +68,9 @@ def child():
 def main():
     vdir = os.path.join(ROOT, "build", "variants")
     names = ["default"] + sorted(n for n in os.listdir(vdir) if os.path.exists(os.path.join(vdir, n, "libvidtome_b200.so"))) if os.path.isdir(vdir) else ["default"]
-    runs = ([(n, {}) for n in names] + [(n + "_no_embed", {"VTM_FA_EMBED": "0"}) for n in names]
-            + [(n + "_groups", {"VTM_FA_GROUPS": "1"}) for n in names if n == "default"])
+    runs = [(n, {}) for n in names]
+    if "--ab" in sys.argv:
+        runs += [(n + "_no_embed", {"VTM_FA_EMBED": "0"}) for n in names] + [("default_groups", {"VTM_FA_GROUPS": "1"})]
     for n, extra in runs:
         env = dict(os.environ, VTM_VARIANT=n, **extra)
         base = n.replace("_no_embed", "").replace("_groups", "")
