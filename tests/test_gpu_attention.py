@@ -27,6 +27,7 @@ def _ref_attention(x, wq, wk, wv, wo, bo, heads, scale):
     (2, 1332, 320, 5),      # head_dim 64 (SD2.x)
     (2, 2561, 640, 8),      # BASELINE config 2, ds2 merged length
     (1, 700, 1024, 8),      # head_dim 128
+    (2, 450, 384, 8),       # head_dim 48 (three k-steps, no spare column)
 ])
 def test_attention_matches_fp32_reference(B, L, C, heads):
     from vidtome_b200 import ops

@@ -221,6 +221,11 @@ __device__ __forceinline__ float fa_row_max(const uint32_t (&r)[NCH][32], int n_
 #ifndef VTM_FA_POLY_DEN
 #define VTM_FA_POLY_DEN 16
 #endif
+// with the embedded reference (MODE 1 / 2: no FFMA in front of the exponential) the balance moves towards the FMA pipe:
+// swept 3 .. 10 of 16, flat minimum at 5 - 7 (profiles/r02_attention_embed_sweep*.jsonl)
+#ifndef VTM_FA_POLY_NUM_EMB
+#define VTM_FA_POLY_NUM_EMB 6
+#endif
 // MODE 0: x = s * c - mc (scores in raw units);  MODE 1: x = s (the scores already ARE the exponents: scale folded into
 // q and the reference embedded in the QK product, see the EMB path of flash_attn_kernel);  MODE 2: x = s - mc.
 template <bool TAIL, bool SUM, int MODE = 0>
@@ -233,7 +238,8 @@ __device__ __forceinline__ void fa_exp32(const uint32_t (&r)[32], uint32_t (&pk)
     const uint64_t x2 = MODE == 0 ? f32x2_fma(s2, c2, nmc2) : (MODE == 1 ? s2 : f32x2_add(s2, nmc2));
     float p0, p1;
     // pair i goes to the polynomial when the running count floor((i+1) NUM / DEN) steps: an even spread
-    if (((i + 1) * VTM_FA_POLY_NUM) / VTM_FA_POLY_DEN != (i * VTM_FA_POLY_NUM) / VTM_FA_POLY_DEN) {
+    constexpr int NUM = MODE == 0 ? VTM_FA_POLY_NUM : VTM_FA_POLY_NUM_EMB;
+    if (((i + 1) * NUM) / VTM_FA_POLY_DEN != (i * NUM) / VTM_FA_POLY_DEN) {
       ex2_poly3_x2(x2, p0, p1);
     } else {
       float x0, x1;
@@ -620,7 +626,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
       uint32_t r[16];
       tmem_ld_32x32b_x16(tmem_o + lane_field + (p.d & ~15), r);
       tmem_ld_wait();
-      l_run = __uint_as_float(r[8]);   // d % 16 == 8
+      l_run = __uint_as_float((p.d & 15) ? r[8] : r[0]);   // column d: d % 16 is 8, or 0 when a k-step was added for it
     }
     if (nparts == 1) {
       // ---- epilogue: O / l -> fp16 -> o[b, row, h*d : h*d + d]
@@ -838,9 +844,9 @@ int launch_fa_impl(const void* qh, const void* kh, const void* vh, __half* o, vo
 
 template <int KSTEPS>
 int launch_fa(const void* qh, const void* kh, const void* vh, __half* o, void* part_ws, int B, int Lq, int L, int C, int H,
-              int d, float scale, int qk_shared, int emb, cudaStream_t stream) {
+              int d, float scale, int qk_shared, int ones, int emb, cudaStream_t stream) {
 #if !defined(VTM_FA_NO_ONES)   // A/B switch: keep the denominator in the softmax warps
-  if (d % 16 == 8)
+  if (ones)
     return launch_fa_impl<KSTEPS, true>(qh, kh, vh, o, part_ws, B, Lq, L, C, H, d, scale, qk_shared, emb, stream);
 #endif
   return launch_fa_impl<KSTEPS, false>(qh, kh, vh, o, part_ws, B, Lq, L, C, H, d, scale, qk_shared, 0, stream);
@@ -849,6 +855,13 @@ int launch_fa(const void* qh, const void* kh, const void* vh, __half* o, void* p
 // The embedded-reference path (flash_attn_kernel EMB) is used when the head dimension leaves a spare column
 // (head_dim % 16 == 8: the SD1.5 full-resolution blocks) and the 2-CTAs-per-SM kernel runs; VTM_FA_EMBED=0 switches
 // it off (A/B measurements).  Read once per process.
+// A spare column for the ones / reference trick exists when head_dim % 16 == 8 (inside the last k-step).  Buying one with an
+// extra k-step when head_dim % 16 == 0 and the padded row is wider (48 -> 4 steps, 80 -> 6) was measured and is NOT taken:
+// head_dim 80, L = 2561: 0.1159 ms with the extra step against 0.1127 ms without (profiles/r02_attention_embed_sweep3.jsonl).
+int fa_ksteps_with_spare(int d, bool* spare) {
+  *spare = d % 16 == 8;
+  return (d + 15) / 16;
+}
 bool fa_use_embed(int d) {
   static const int v = [] {
     const char* e = getenv("VTM_FA_EMBED");
@@ -857,17 +870,22 @@ bool fa_use_embed(int d) {
 #if defined(VTM_FA_NO_ONES)
   return false;
 #endif
-  return v != 0 && d % 16 == 8 && !fa_use_groups();
+  bool spare = false;
+  fa_ksteps_with_spare(d, &spare);
+  return v != 0 && spare && !fa_use_groups();
 }
 
 int launch_fa_any(const void* qh, const void* kh, const void* vh, __half* o, void* part_ws, int B, int Lq, int L, int C,
                   int H, int d, float scale, int qk_shared, int emb, cudaStream_t stream) {
-  switch ((d + 15) / 16) {
-    case 1: case 2: case 3: return launch_fa<3>(qh, kh, vh, o, part_ws, B, Lq, L, C, H, d, scale, qk_shared, emb, stream);
-    case 4: return launch_fa<4>(qh, kh, vh, o, part_ws, B, Lq, L, C, H, d, scale, qk_shared, emb, stream);
-    case 5: return launch_fa<5>(qh, kh, vh, o, part_ws, B, Lq, L, C, H, d, scale, qk_shared, emb, stream);
-    case 6: return launch_fa<6>(qh, kh, vh, o, part_ws, B, Lq, L, C, H, d, scale, qk_shared, emb, stream);
-    default: return launch_fa<8>(qh, kh, vh, o, part_ws, B, Lq, L, C, H, d, scale, qk_shared, emb, stream);
+  bool spare = false;
+  const int ks = fa_ksteps_with_spare(d, &spare);
+  const int ones = spare ? 1 : 0;
+  switch (ks) {
+    case 1: case 2: case 3: return launch_fa<3>(qh, kh, vh, o, part_ws, B, Lq, L, C, H, d, scale, qk_shared, ones, emb, stream);
+    case 4: return launch_fa<4>(qh, kh, vh, o, part_ws, B, Lq, L, C, H, d, scale, qk_shared, ones, emb, stream);
+    case 5: return launch_fa<5>(qh, kh, vh, o, part_ws, B, Lq, L, C, H, d, scale, qk_shared, ones, emb, stream);
+    case 6: return launch_fa<6>(qh, kh, vh, o, part_ws, B, Lq, L, C, H, d, scale, qk_shared, ones, emb, stream);
+    default: return launch_fa<8>(qh, kh, vh, o, part_ws, B, Lq, L, C, H, d, scale, qk_shared, ones, emb, stream);
   }
 }
 

@@ -332,7 +332,7 @@ flash_attn_groups_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
           uint32_t rr[16];
           tmem_ld_32x32b_x16(tmem_base + lane_field + C::o_col(g) + (p.d & ~15), rr);
           tmem_ld_wait();
-          l = fmaf(w[g], __uint_as_float(rr[8]), l);   // d % 16 == 8
+          l = fmaf(w[g], __uint_as_float((p.d & 15) ? rr[8] : rr[0]), l);   // column d
         }
       }
     }
