@@ -73,45 +73,85 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 50 ms during the timed region."""
+    """SM clock and throttle reasons sampled during the timed region: NVML in-process every 10 ms (pynvml; a 0.2 s timed
+    region still gets ~20 samples), `nvidia-smi -lms 50` as the fallback when NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    # nvmlClocksThrottleReason* bit masks (nvml.h)
+    BITS = (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
 
-    def __init__(self, index: int):
-        self.rows, self.proc = [], None
+    def __init__(self, index: int, uuid: str = ""):
+        self.rows, self.proc, self.mode = [], None, None       # rows: (sm_mhz, max_mhz, set(reasons))
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if uuid:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+                except Exception:
+                    h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        mask = int(reasons_fn(h))
+                        self.rows.append((sm, mx, {n for n, b in self.BITS if mask & b}))
+                    except Exception:
+                        pass
+                    self._stop.wait(0.01)
+            self.thr = threading.Thread(target=loop, daemon=True)
+            self.thr.start()
+            self.mode = "nvml"
+            return
+        except Exception:
+            pass
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
+            self.mode = "nvidia-smi"
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        for r in self.rows:
+            r = [c.strip() for c in line.split(",")]
             try:
-                sm.append(float(r[0])); mx = float(r[1])
+                sm, mx = float(r[0]), float(r[1])
             except Exception:
                 continue
-            for name, col in (("hw_slowdown", 4), ("hw_thermal_slowdown", 5), ("sw_thermal_slowdown", 6), ("sw_power_cap", 7)):
-                if len(r) > col and r[col].lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
+            names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+            self.rows.append((sm, mx, {n for n, c in zip(names, (4, 5, 6, 7)) if len(r) > c and r[c].lower().startswith("active")}))
+
+    def count(self):
+        return len(self.rows)
+
+    def stop(self):
+        if self.mode is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml / nvidia-smi unavailable"], "samples": 0}
+        if self.mode == "nvidia-smi":
+            time.sleep(0.25)
+            self.proc.terminate()
+        self._stop.set()
+        rows = list(self.rows)
+        sm = sorted(r[0] for r in rows)
+        mx = rows[-1][1] if rows else None
+        reasons = set().union(*[r[2] for r in rows]) if rows else set()
         # median over samples under load (idle samples at the edges report the idle clock)
         load = [v for v in sm if mx and v > 0.4 * mx] or sm
         return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": self.mode}
 
 
 # ------------------------------------------------------------------------------------------------ CPU legs
@@ -426,9 +466,19 @@ def run_ours(args):
     warm = max(3, args.warmup)
     for i in range(warm + 2):                                  # 2 eager steps, capture, then >= 3 replays
         dev_step(i)
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local, str(getattr(torch.cuda.get_device_properties(local), "uuid", "") or "")) if rank == 0 else None
     ms = timed(dev_step, args.steps)
+    if sampler and world == 1 and sampler.mode is not None:
+        # a timed region shorter than the sampler's period: keep the SAME workload running (untimed) until it has
+        # a few samples under load, and say so
+        t_end, extra = time.time() + 3.0, 0
+        while sampler.count() < 5 and time.time() < t_end:
+            dev_step(extra)
+            torch.cuda.synchronize()
+            extra += 1
     clocks = sampler.stop() if sampler else None
+    if clocks is not None and sampler and world == 1:
+        clocks["untimed_continuation_steps"] = extra if sampler.mode is not None else 0
     for i in range(3):
         e2e_step(i)
     ms_e2e = timed(e2e_step, args.steps)

@@ -22,6 +22,7 @@
 // TMEM (256 columns): S0/P0 [0,BKV) | S1/P1 [BKV,2 BKV) | O [2 BKV, 2 BKV + 16*KSTEPS); BKV = 96 keys per tile when
 // that fits (head_dim <= 64), else 64.
 #include <stdlib.h>
+#include <type_traits>
 
 #include "gemm_sm100.cuh"
 
@@ -149,7 +150,12 @@ int launch_qkv_heads(const void* x, const void* w_qkv, __half* qkvh, int B, int 
 __device__ unsigned int vtm_fa_sm_slot[256];
 
 constexpr int BQ = 128;    // query rows per CTA (UMMA M)
-constexpr int FA_THREADS = 192;
+#ifndef VTM_FA_PAIRS_DEFAULT
+#define VTM_FA_PAIRS_DEFAULT 0
+#endif
+constexpr int FA_THREADS = 192;        // TMA warp, MMA warp, four softmax warps
+constexpr int FA_PAIR_THREADS = 320;   // ... eight softmax warps (flash_attn_kernel HALVES = 2)
+constexpr uint32_t FA_PAIR_XCH_BYTES = 2048;   // [quadrant 4][slot 2][half 2][lane 32] floats
 constexpr float RESCALE_LOG2 = 8.f;   // move the reference max only when exceeded by 2^8
 
 struct FaParams {
@@ -259,6 +265,33 @@ __device__ __forceinline__ void fa_exp32(const uint32_t (&r)[32], uint32_t (&pk)
   }
 }
 
+// The same for N raw exponents held in a plain register array (pair kernel below): MODE 1 (x = s) or 2 (x = s - mc);
+// PAIR0 = index of the first pair in the thread's tile share, so that the polynomial pairs stay evenly spread.
+template <int N, int PAIR0, bool TAIL, int MODE>
+__device__ __forceinline__ void fa_exp_n(const uint32_t* r, uint32_t* pk, float mc, int n_valid) {
+  const uint64_t nmc2 = f32x2_pack(-mc, -mc);
+#pragma unroll
+  for (int i = 0; i < N / 2; ++i) {
+    const uint64_t s2 = f32x2_pack(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+    const uint64_t x2 = MODE == 1 ? s2 : f32x2_add(s2, nmc2);
+    float p0, p1;
+    const int g = PAIR0 + i;
+    if (((g + 1) * VTM_FA_POLY_NUM_EMB) / VTM_FA_POLY_DEN != (g * VTM_FA_POLY_NUM_EMB) / VTM_FA_POLY_DEN) {
+      ex2_poly3_x2(x2, p0, p1);
+    } else {
+      float x0, x1;
+      f32x2_unpack(x2, x0, x1);
+      p0 = ex2_approx(x0);
+      p1 = ex2_approx(x1);
+    }
+    if (TAIL) {
+      if (2 * (PAIR0 + i) >= n_valid) p0 = 0.f;
+      if (2 * (PAIR0 + i) + 1 >= n_valid) p1 = 0.f;
+    }
+    pk[i] = pack_f16x2(p0, p1);
+  }
+}
+
 // ONES: head_dim % 16 == 8 (40, the SD1.5 full-resolution blocks): column d of the padded V rows holds 1.0 and lies
 // inside the P V MMA's N, so O[:, d] accumulates the row sums of P — the denominator comes out of the tensor core,
 // follows every rescale of O automatically and is the sum of exactly the fp16 P values the numerator uses; the
@@ -271,8 +304,15 @@ __device__ __forceinline__ void fa_exp32(const uint32_t (&r)[32], uint32_t (&pk)
 // reference: it rewrites the 2-byte column in shared memory (swizzled address) when the reference moves — after the one
 // QK MMA that may still be reading the tile has completed (s_full of the next tile) — and keeps track of which reference
 // each tile's scores embed (QK runs one tile ahead, so a new reference takes effect two tiles later).
-template <int KSTEPS, bool ONES, bool EMB = false>
-__global__ void __launch_bounds__(FA_THREADS, FaCfg<KSTEPS>::MIN_CTAS)
+// HALVES == 2 (requires EMB): EIGHT softmax warps per CTA, two per 32-row TMEM quadrant, each taking one half of the tile's
+// keys of the same rows — four softmax warps per scheduler instead of two to cover the fixed-latency dependencies that
+// dominate the stall samples (profiles/r02_attention_kernel_study.md section 7).  With the denominator coming out of the P V MMA
+// (ONES) and the reference embedded in the scores (EMB) the only thing the two warps of a row share is the decision "the
+// reference moves" — one bar.red.or over the 64 threads per tile in the steady state, plus an exchange of the two half-row
+// maxima through shared memory on the rare tiles where it does.  Each half writes its P into the first half of ITS OWN score
+// columns (so no warp overwrites scores the other has not read yet); the P V MMAs take their A operand from the two pieces.
+template <int KSTEPS, bool ONES, bool EMB = false, int HALVES = 1>
+__global__ void __launch_bounds__(HALVES == 2 ? FA_PAIR_THREADS : FA_THREADS, FaCfg<KSTEPS>::MIN_CTAS)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                   const __grid_constant__ CUtensorMap tm_v, const FaParams p) {
   using C = FaCfg<KSTEPS>;
@@ -326,7 +366,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(s_full(i), 1);
-      mbar_init(p_full(i), 4);  // one arrival per softmax warp
+      mbar_init(p_full(i), 4 * HALVES);  // one arrival per softmax warp
     }
     mbar_init(o_ready(0), 1);
     mbar_init(o_ready(1), 1);
@@ -398,14 +438,18 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
       const uint32_t p_tmem = tmem_base + (j & 1) * BKV;
       if (elect_one()) {
         const uint64_t vdesc = umma_desc_sw128_mnmajor(sv, C::KV_ATOM);
+        // P of keys 16 t .. 16 t + 15: 8 packed columns; HALVES == 2: the second half of the keys starts at column BKV / 2
+        auto p_col = [&](int t) -> uint32_t {
+          return HALVES == 2 && t >= BKV / 32 ? static_cast<uint32_t>(BKV / 2 + 8 * (t - BKV / 32)) : 8u * t;
+        };
         if (j == 0) {
 #pragma unroll
           for (int t = 0; t < BKV / 16; ++t)
-            umma_f16_ts(tmem_o, p_tmem + 8u * t, vdesc + 128u * t, idesc_pv, t != 0 ? 1u : 0u);
+            umma_f16_ts(tmem_o, p_tmem + p_col(t), vdesc + 128u * t, idesc_pv, t != 0 ? 1u : 0u);
         } else {
 #pragma unroll
           for (int t = 0; t < BKV / 16; ++t)
-            umma_f16_ts(tmem_o, p_tmem + 8u * t, vdesc + 128u * t /* 16 rows x 128 B */, idesc_pv, 1u);
+            umma_f16_ts(tmem_o, p_tmem + p_col(t), vdesc + 128u * t /* 16 rows x 128 B */, idesc_pv, 1u);
         }
         umma_commit(kv_empty(s));
         umma_commit(o_ready(j & 1));
@@ -414,7 +458,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     }
   } else {
     // ===================== softmax / correction / epilogue =====================
-    const int quad = warp & 3;
+    const int quad = warp & 3;                                   // TMEM lane quadrant this warp may access
+    const int half = HALVES == 2 ? ((warp - 2) >> 2) : 0;        // which half of a tile's keys (HALVES == 2)
     const int row = q0 + quad * 32 + lane;
     const uint32_t lane_field = static_cast<uint32_t>(quad * 32) << 16;
     const float c = p.scale_log2;
@@ -428,16 +473,154 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
       uint32_t smid;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
       uint32_t slot = 0;
-      if (lane == 0 && quad == 0) slot = atomicAdd(&vtm_fa_sm_slot[smid & 255u], 1u);
-      // one draw per CTA, broadcast to the four softmax warps through the (already initialised) tmem pointer slot + 4
-      if (lane == 0 && quad == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(tmem_ptr_addr + 4), "r"(slot) : "memory");
-      asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (lane == 0 && warp == 2) slot = atomicAdd(&vtm_fa_sm_slot[smid & 255u], 1u);
+      // one draw per CTA, broadcast to the softmax warps through the (already initialised) tmem pointer slot + 4
+      if (lane == 0 && warp == 2) asm volatile("st.shared.u32 [%0], %1;" ::"r"(tmem_ptr_addr + 4), "r"(slot) : "memory");
+      bar_sync_named(2, 128 * HALVES);
       asm volatile("ld.shared.u32 %0, [%1];" : "=r"(slot) : "r"(tmem_ptr_addr + 4));
       if (slot & 1u) __nanosleep(VTM_FA2_STAGGER_NS);
     }
 #endif
+    if constexpr (EMB && HALVES == 2) {
+      constexpr int HK = BKV / 2;          // keys per half tile
+      constexpr int NB = HK - 32;          // scores beyond the first 32 of the half: 16 (BKV = 96) or 0 (BKV = 64)
+      static_assert(NB == 0 || NB == 16, "half tiles of 32 or 48 keys");
+      const int rit = quad * 32 + lane;
+      const int dcol = p.d & 63, datom = p.d >> 6;
+      const uint32_t q_ref_addr = sQ + datom * (BQ * 128) + rit * 128 + ((((2 * dcol) >> 4) ^ (rit & 7)) << 4) + ((2 * dcol) & 15);
+      const uint32_t xch = bar_base + 256u + static_cast<uint32_t>(quad) * 512u;   // [slot][half][lane] floats of this quadrant
+      const uint32_t bar_id = 3u + quad;   // named barrier of the two warps of this quadrant (0: __syncthreads, 2: stagger)
+      float m_O = -INFINITY, e_tile0 = 0.f, e_tile1 = 0.f, e_q = 0.f;   // as in the HALVES == 1 loop; identical in both halves
+      for (int j = 0; j < nkv; ++j) {
+        mbar_wait(s_full(j & 1), (j >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t s_addr = tmem_base + lane_field + (j & 1) * BKV + half * HK;   // my scores; my P goes to their first half
+        const int n_tile = p.L - (j_lo + j) * BKV;
+        const bool tail = n_tile < BKV;
+        const int n_valid = n_tile - half * HK;        // existing keys of my half (<= 0: none)
+        uint32_t ra[32], rb[NB > 0 ? NB : 1];
+        const float e = (j & 1) ? e_tile1 : e_tile0;
+        float mx;
+        bool slow;
+        if (j == 0 || tail) {
+          tmem_ld_32x32b_x32(s_addr, ra);
+          if constexpr (NB > 0) tmem_ld_32x32b_x16(s_addr + 32, rb);
+          tmem_ld_wait();
+          float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            if (!tail || i < n_valid) m0 = fmaxf(m0, __uint_as_float(ra[i]));
+            if (!tail || i + 1 < n_valid) m1 = fmaxf(m1, __uint_as_float(ra[i + 1]));
+          }
+          if constexpr (NB > 0) {
+#pragma unroll
+            for (int i = 0; i < NB; i += 2) {
+              if (!tail || 32 + i < n_valid) m0 = fmaxf(m0, __uint_as_float(rb[i]));
+              if (!tail || 33 + i < n_valid) m1 = fmaxf(m1, __uint_as_float(rb[i + 1]));
+            }
+          }
+          mx = fmaxf(m0, m1);
+          slow = true;
+        } else {
+          // speculative, as in the HALVES == 1 loop: the scores are the exponents while the tile embeds O's reference and
+          // no score of the ROW (both halves) exceeds it by more than 2^8
+          float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+          tmem_ld_32x32b_x32(s_addr, ra);
+          tmem_ld_wait();
+          if constexpr (NB > 0) tmem_ld_32x32b_x16(s_addr + 32, rb);
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            m0 = fmax3(m0, __uint_as_float(ra[i]), __uint_as_float(ra[i + 1]));
+            m1 = fmax3(m1, __uint_as_float(ra[i + 2]), __uint_as_float(ra[i + 3]));
+            m2 = fmax3(m2, __uint_as_float(ra[i + 4]), __uint_as_float(ra[i + 5]));
+            m3 = fmax3(m3, __uint_as_float(ra[i + 6]), __uint_as_float(ra[i + 7]));
+          }
+          {
+            uint32_t pk[16];
+            fa_exp_n<32, 0, false, 1>(ra, pk, 0.f, n_valid);
+            tmem_st_32x32b_x16(s_addr, pk);
+          }
+          if constexpr (NB > 0) {
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < NB; i += 8) {
+              m0 = fmax3(m0, __uint_as_float(rb[i]), __uint_as_float(rb[i + 1]));
+              m1 = fmax3(m1, __uint_as_float(rb[i + 2]), __uint_as_float(rb[i + 3]));
+              m2 = fmax3(m2, __uint_as_float(rb[i + 4]), __uint_as_float(rb[i + 5]));
+              m3 = fmax3(m3, __uint_as_float(rb[i + 6]), __uint_as_float(rb[i + 7]));
+            }
+            uint32_t pk8[NB / 2];
+            fa_exp_n<NB, 16, false, 1>(rb, pk8, 0.f, n_valid);
+            tmem_st_32x32b_x8(s_addr + 16, pk8);
+          }
+          mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+          slow = bar_red_or(bar_id, 64, !(e == m_O && mx <= RESCALE_LOG2));   // over both warps of the quadrant
+        }
+        float alpha = 1.f;
+        if (slow) {
+          // the row maximum over both halves (slots alternate with j: a warp may enter its next slow tile before the other
+          // has read this one's value; two tiles later the barrier of the tile in between orders them)
+          const uint32_t slot = xch + static_cast<uint32_t>(j & 1) * 256u;
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(slot + (half * 32 + lane) * 4), "f"(mx) : "memory");
+          bar_sync_named(bar_id, 64);
+          float other;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(slot + ((half ^ 1) * 32 + lane) * 4) : "memory");
+          mx = fmaxf(mx, other);
+          const float abs_max = e + mx;
+          float r_new = m_O;
+          if (!(abs_max - m_O <= RESCALE_LOG2)) r_new = __half2float(__float2half_ru(abs_max));
+          if (r_new != m_O) {
+            alpha = ex2_approx(m_O - r_new);
+            m_O = r_new;
+          }
+          const float delta = m_O - e;
+          uint32_t pk[16];
+          if (tail) fa_exp_n<32, 0, true, 2>(ra, pk, delta, n_valid);
+          else fa_exp_n<32, 0, false, 2>(ra, pk, delta, n_valid);
+          tmem_st_32x32b_x16(s_addr, pk);
+          if constexpr (NB > 0) {
+            uint32_t pk8[NB / 2];
+            if (tail) fa_exp_n<NB, 16, true, 2>(rb, pk8, delta, n_valid);
+            else fa_exp_n<NB, 16, false, 2>(rb, pk8, delta, n_valid);
+            tmem_st_32x32b_x8(s_addr + 16, pk8);
+          }
+        }
+        if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {     // same alpha in both halves: they share the O chunks
+          mbar_wait(o_ready((j - 1) & 1), ((j - 1) >> 1) & 1u);
+          tc_fence_after();
+#pragma unroll
+          for (int cb = 0; cb < C::DV_N; cb += 16) {
+            if (((cb >> 4) & 1) != half) continue;
+            uint32_t ro[16];
+            tmem_ld_32x32b_x16(tmem_o + lane_field + cb, ro);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
+            tmem_st_32x32b_x16(tmem_o + lane_field + cb, ro);
+          }
+        }
+        if (j + 2 < nkv && __any_sync(0xffffffffu, e_q != m_O)) {
+          if (half == 0) {                 // half 0 owns the row's reference column in shared memory
+            mbar_wait(s_full((j + 1) & 1), ((j + 1) >> 1) & 1u);
+            if (e_q != m_O) {
+              const unsigned short neg = __half_as_ushort(__float2half_rn(-m_O));
+              asm volatile("st.shared.u16 [%0], %1;" ::"r"(q_ref_addr), "h"(neg) : "memory");
+            }
+            fence_proxy_async_smem();
+          }
+          e_q = m_O;
+        }
+        if (j & 1) e_tile1 = e_q; else e_tile0 = e_q;
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full(j & 1));
+      }
+      m_ref = m_O;
+    } else
     if constexpr (EMB) {
       static_assert(ONES, "the embedded reference uses the spare column of head_dim % 16 == 8");
+      static_assert(HALVES == 1, "HALVES == 2 has its own loop above");
       const int rit = quad * 32 + lane;                                  // row in the Q tile
       const int dcol = p.d & 63, datom = p.d >> 6;                       // column d inside its 64-wide block
       const uint32_t q_ref_addr = sQ + datom * (BQ * 128) + rit * 128 + ((((2 * dcol) >> 4) ^ (rit & 7)) << 4) + ((2 * dcol) & 15);
@@ -445,18 +628,24 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
       float e_tile0 = 0.f, e_tile1 = 0.f;   // reference embedded in the scores of tile j (j even / odd)
       float e_q = 0.f;                 // reference currently in shared memory (embedded from tile j + 2 on)
       float dummy0 = 0.f, dummy1 = 0.f;
-      for (int j = 0; j < nkv; ++j) {
+      // One key tile.  PLAIN = first tile of the unit (no reference yet) or its last one (possibly masked columns): row
+      // maximum first, then the exponentials.  The steady-state tiles in between are instantiated separately so that their
+      // loop body holds nothing but the speculative path and ONE warp-uniform branch around everything rare (reference
+      // moved: recompute P, rescale O, republish the reference) — the instruction-fetch stalls after the taken branches of
+      // the single-loop version were 7 % of the softmax warps' samples (profiles/r02_attention_kernel_study.md section 7).
+      auto tile_step = [&](const int j, auto plain_c) {
+        constexpr bool PLAIN = decltype(plain_c)::value;
         mbar_wait(s_full(j & 1), (j >> 1) & 1u);
         tc_fence_after();
         const uint32_t s_addr = tmem_base + lane_field + (j & 1) * BKV;
         const int n_valid = p.L - (j_lo + j) * BKV;
-        const bool tail = n_valid < BKV;
+        const bool tail = PLAIN && n_valid < BKV;
         constexpr int NCH = BKV / 32;
         uint32_t r[NCH][32];
         const float e = (j & 1) ? e_tile1 : e_tile0;
         float mx;
         bool slow;
-        if (j == 0 || tail) {
+        if constexpr (PLAIN) {
 #pragma unroll
           for (int ch = 0; ch < NCH; ++ch) tmem_ld_32x32b_x32(s_addr + 32 * ch, r[ch]);
           tmem_ld_wait();
@@ -482,58 +671,64 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             tmem_st_32x32b_x16(s_addr + 16 * ch, pk);
           }
           mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-          slow = __any_sync(0xffffffffu, !(e == m_O && mx <= RESCALE_LOG2));
+          slow = !(e == m_O && mx <= RESCALE_LOG2);
         }
-        float alpha = 1.f;
-        if (slow) {
-          // settle the reference for this tile: keep O's unless the row maximum exceeds it by more than 2^8, then move
-          // it to the maximum (rounded UP to fp16 so that it can be embedded exactly)
-          const float abs_max = e + mx;
-          float r_new = m_O;
-          if (!(abs_max - m_O <= RESCALE_LOG2)) r_new = __half2float(__float2half_ru(abs_max));   // also the first tile (m_O = -inf)
-          if (r_new != m_O) {
-            alpha = ex2_approx(m_O - r_new);       // 0 on the first tile
-            m_O = r_new;
-          }
-          const float delta = m_O - e;              // exponent = s' - delta
+        // everything below the speculative path is rare after the first tiles: one warp-uniform branch around it
+        if (PLAIN || __any_sync(0xffffffffu, slow || e_q != m_O)) {
+          float alpha = 1.f;
+          if (PLAIN || __any_sync(0xffffffffu, slow)) {
+            // settle the reference for this tile: keep O's unless the row maximum exceeds it by more than 2^8, then move
+            // it to the maximum (rounded UP to fp16 so that it can be embedded exactly)
+            const float abs_max = e + mx;
+            float r_new = m_O;
+            if (!(abs_max - m_O <= RESCALE_LOG2)) r_new = __half2float(__float2half_ru(abs_max));   // also the first tile (m_O = -inf)
+            if (r_new != m_O) {
+              alpha = ex2_approx(m_O - r_new);       // 0 on the first tile
+              m_O = r_new;
+            }
+            const float delta = m_O - e;              // exponent = s' - delta
 #pragma unroll
-          for (int ch = 0; ch < NCH; ++ch) {
-            uint32_t pk[16];
-            if (tail) fa_exp32<true, false, 2>(r[ch], pk, 0.f, delta, 32 * ch, n_valid, dummy0, dummy1);
-            else fa_exp32<false, false, 2>(r[ch], pk, 0.f, delta, 32 * ch, n_valid, dummy0, dummy1);
-            tmem_st_32x32b_x16(s_addr + 16 * ch, pk);
+            for (int ch = 0; ch < NCH; ++ch) {
+              uint32_t pk[16];
+              if (tail) fa_exp32<true, false, 2>(r[ch], pk, 0.f, delta, 32 * ch, n_valid, dummy0, dummy1);
+              else fa_exp32<false, false, 2>(r[ch], pk, 0.f, delta, 32 * ch, n_valid, dummy0, dummy1);
+              tmem_st_32x32b_x16(s_addr + 16 * ch, pk);
+            }
           }
-        }
-        if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
-          mbar_wait(o_ready((j - 1) & 1), ((j - 1) >> 1) & 1u);
-          tc_fence_after();
+          if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+            mbar_wait(o_ready((j - 1) & 1), ((j - 1) >> 1) & 1u);
+            tc_fence_after();
 #pragma unroll
-          for (int cb = 0; cb < C::DV_N; cb += 16) {
-            uint32_t ro[16];
-            tmem_ld_32x32b_x16(tmem_o + lane_field + cb, ro);
-            tmem_ld_wait();
+            for (int cb = 0; cb < C::DV_N; cb += 16) {
+              uint32_t ro[16];
+              tmem_ld_32x32b_x16(tmem_o + lane_field + cb, ro);
+              tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
-            tmem_st_32x32b_x16(tmem_o + lane_field + cb, ro);
+              for (int i = 0; i < 16; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
+              tmem_st_32x32b_x16(tmem_o + lane_field + cb, ro);
+            }
           }
-        }
-        // publish O's reference for the tiles whose QK has not been issued yet (j + 2 onwards)
-        if (j + 2 < nkv && __any_sync(0xffffffffu, e_q != m_O)) {
-          // QK of tile j + 1 (issued with the old column) may still be reading this Q tile: wait for its commit
-          mbar_wait(s_full((j + 1) & 1), ((j + 1) >> 1) & 1u);
-          if (e_q != m_O) {
-            const unsigned short neg = __half_as_ushort(__float2half_rn(-m_O));
-            asm volatile("st.shared.u16 [%0], %1;" ::"r"(q_ref_addr), "h"(neg) : "memory");
-            e_q = m_O;
+          // publish O's reference for the tiles whose QK has not been issued yet (j + 2 onwards)
+          if (j + 2 < nkv && __any_sync(0xffffffffu, e_q != m_O)) {
+            // QK of tile j + 1 (issued with the old column) may still be reading this Q tile: wait for its commit
+            mbar_wait(s_full((j + 1) & 1), ((j + 1) >> 1) & 1u);
+            if (e_q != m_O) {
+              const unsigned short neg = __half_as_ushort(__float2half_rn(-m_O));
+              asm volatile("st.shared.u16 [%0], %1;" ::"r"(q_ref_addr), "h"(neg) : "memory");
+              e_q = m_O;
+            }
+            fence_proxy_async_smem();    // generic-proxy store -> visible to the tensor core's (async proxy) operand reads
           }
-          fence_proxy_async_smem();    // generic-proxy store -> visible to the tensor core's (async proxy) operand reads
         }
         if (j & 1) e_tile1 = e_q; else e_tile0 = e_q;     // what tile j + 2 will embed
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full(j & 1));
-      }
+      };
+      tile_step(0, std::true_type{});
+      for (int j = 1; j + 1 < nkv; ++j) tile_step(j, std::false_type{});
+      if (nkv > 1) tile_step(nkv - 1, std::true_type{});
       m_ref = m_O;      // log2 units already (see the partial-result store below)
     } else
     for (int j = 0; j < nkv; ++j) {
@@ -634,6 +829,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
       __half* orow = p.o + (static_cast<size_t>(b) * p.Lq + row) * p.C + h * p.d;
 #pragma unroll
       for (int cb = 0; cb < C::DV_N; cb += 16) {
+        if (HALVES == 2 && ((cb >> 4) & 1) != half) continue;     // the two warps of a row share the output chunks
         uint32_t r[16];
         tmem_ld_32x32b_x16(tmem_o + lane_field + cb, r);
         tmem_ld_wait();
@@ -657,10 +853,11 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     } else {
       // ---- split tile: un-normalised O, reference max and denominator of this key range
       const size_t prow = (static_cast<size_t>(tile - p.n_full) * nparts + part) * BQ + quad * 32 + lane;
-      p.part_ml[prow] = make_float2(EMB ? m_ref : m_ref * c, l_run);
+      if (half == 0) p.part_ml[prow] = make_float2(EMB ? m_ref : m_ref * c, l_run);
       float* po = p.part_o + prow * C::DV_N;
 #pragma unroll
       for (int cb = 0; cb < C::DV_N; cb += 16) {
+        if (HALVES == 2 && ((cb >> 4) & 1) != half) continue;
         uint32_t r[16];
         tmem_ld_32x32b_x16(tmem_o + lane_field + cb, r);
         tmem_ld_wait();
@@ -741,6 +938,14 @@ bool fa_use_groups() {
   }();
   return v != 0;
 }
+// VTM_FA_PAIRS=0 keeps four softmax warps per CTA on the embedded-reference path (flash_attn_kernel HALVES = 1) for A/B runs.
+bool fa_use_pairs() {
+  static const int v = [] {
+    const char* e = getenv("VTM_FA_PAIRS");
+    return e ? (e[0] == '1' ? 1 : 0) : VTM_FA_PAIRS_DEFAULT;
+  }();
+  return v != 0;
+}
 int fa_forced_splits() {
   static const int v = [] {
     const char* e = getenv("VTM_FA_SPLITS");   // tuning override (tools/sweep_fa_splits.py)
@@ -786,6 +991,11 @@ int launch_fa_impl(const void* qh, const void* kh, const void* vh, __half* o, vo
                                         static_cast<int>(Cf::SMEM_BYTES)));
       if (rc) return rc;
     }
+    if constexpr (ONES && KSTEPS == 3) {
+      rc = cuda_rc(cudaFuncSetAttribute(flash_attn_kernel<KSTEPS, true, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(Cf::SMEM_BYTES + FA_PAIR_XCH_BYTES)));
+      if (rc) return rc;
+    }
     rc = cuda_rc(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, flash_attn_kernel<KSTEPS, ONES>, FA_THREADS,
                                                                Cf::SMEM_BYTES));
     if (rc) return rc;
@@ -829,7 +1039,16 @@ int launch_fa_impl(const void* qh, const void* kh, const void* vh, __half* o, vo
   p.part_o = reinterpret_cast<float*>(static_cast<char*>(part_ws) +
                                       static_cast<size_t>(FA_MAX_SPLIT_UNITS) * BQ * sizeof(float2));
   const long long units = p.n_full + (tiles - p.n_full) * splits;
-  if (groups)
+  bool launched = false;
+  if constexpr (ONES && KSTEPS == 3) {
+    if (!groups && emb && fa_use_pairs()) {
+      flash_attn_kernel<KSTEPS, true, true, 2>
+          <<<static_cast<unsigned>(units), FA_PAIR_THREADS, Cf::SMEM_BYTES + FA_PAIR_XCH_BYTES, stream>>>(tq, tk, tv, p);
+      launched = true;
+    }
+  }
+  if (launched) {
+  } else if (groups)
     flash_attn_groups_kernel<KSTEPS, ONES><<<static_cast<unsigned>(units), Cg::THREADS, Cg::SMEM_BYTES, stream>>>(tq, tk, tv, p);
   else if (ONES && emb)
     flash_attn_kernel<KSTEPS, ONES, ONES><<<static_cast<unsigned>(units), FA_THREADS, Cf::SMEM_BYTES, stream>>>(tq, tk, tv, p);
