@@ -730,18 +730,20 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
       for (int j = 1; j + 1 < nkv; ++j) tile_step(j, std::false_type{});
       if (nkv > 1) tile_step(nkv - 1, std::true_type{});
       m_ref = m_O;      // log2 units already (see the partial-result store below)
-    } else
-    for (int j = 0; j < nkv; ++j) {
+    } else {
+    // same split as the EMB loop above: first / last tile on the plain path, the steady-state tiles in a loop of their own
+    auto tile_step = [&](const int j, auto plain_c) {
+      constexpr bool PLAIN = decltype(plain_c)::value;
       mbar_wait(s_full(j & 1), (j >> 1) & 1u);
       tc_fence_after();
       const uint32_t s_addr = tmem_base + lane_field + (j & 1) * BKV;
       const int n_valid = p.L - (j_lo + j) * BKV;  // keys of this tile that exist
-      const bool tail = n_valid < BKV;
+      const bool tail = PLAIN && n_valid < BKV;
       constexpr int NCH = BKV / 32;
       uint32_t r[NCH][32];   // the row's scores, read from TMEM exactly once
       float alpha = 1.f, sum0 = 0.f, sum1 = 0.f;
       bool redo;
-      if (j == 0 || tail) {
+      if constexpr (PLAIN) {
         // ---- plain path (first tile: no reference yet; last tile: masked columns): max first, then exponentials
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) tmem_ld_32x32b_x32(s_addr + 32 * ch, r[ch]);
@@ -783,7 +785,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
           m_ref = mx;
         }
       }
-      if (redo) {
+      if (redo) {     // one branch around everything rare: recompute P, rescale O
         const float mc = m_ref * c;
         sum0 = 0.f;
         sum1 = 0.f;
@@ -794,26 +796,30 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
           else fa_exp32<false, !ONES>(r[ch], pk, c, mc, 32 * ch, n_valid, sum0, sum1);
           tmem_st_32x32b_x16(s_addr + 16 * ch, pk);
         }
-      }
-      if (!ONES) l_run = l_run * alpha + (sum0 + sum1);
-      // ---- O rescale: only when a reference max moved, and only after P_{j-1} V_{j-1} has retired
-      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
-        mbar_wait(o_ready((j - 1) & 1), ((j - 1) >> 1) & 1u);
-        tc_fence_after();
+        // ---- O rescale: only when a reference max moved, and only after P_{j-1} V_{j-1} has retired
+        if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+          mbar_wait(o_ready((j - 1) & 1), ((j - 1) >> 1) & 1u);
+          tc_fence_after();
 #pragma unroll
-        for (int cb = 0; cb < C::DV_N; cb += 16) {
-          uint32_t ro[16];
-          tmem_ld_32x32b_x16(tmem_o + lane_field + cb, ro);
-          tmem_ld_wait();
+          for (int cb = 0; cb < C::DV_N; cb += 16) {
+            uint32_t ro[16];
+            tmem_ld_32x32b_x16(tmem_o + lane_field + cb, ro);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
-          tmem_st_32x32b_x16(tmem_o + lane_field + cb, ro);
+            for (int i = 0; i < 16; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
+            tmem_st_32x32b_x16(tmem_o + lane_field + cb, ro);
+          }
         }
       }
+      if (!ONES) l_run = l_run * alpha + (sum0 + sum1);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full(j & 1));
+    };
+    tile_step(0, std::true_type{});
+    for (int j = 1; j + 1 < nkv; ++j) tile_step(j, std::false_type{});
+    if (nkv > 1) tile_step(nkv - 1, std::true_type{});
     }
     mbar_wait(o_ready((nkv - 1) & 1), ((nkv - 1) >> 1) & 1u);
     tc_fence_after();
