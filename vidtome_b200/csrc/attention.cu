@@ -633,102 +633,126 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
       // loop body holds nothing but the speculative path and ONE warp-uniform branch around everything rare (reference
       // moved: recompute P, rescale O, republish the reference) — the instruction-fetch stalls after the taken branches of
       // the single-loop version were 7 % of the softmax warps' samples (profiles/r02_attention_kernel_study.md section 7).
-      auto tile_step = [&](const int j, auto plain_c) {
-        constexpr bool PLAIN = decltype(plain_c)::value;
+      constexpr int NCH = BKV / 32;
+      uint32_t r[NCH][32];             // the row's raw scores of the tile in flight (kept for the rare recomputation)
+      float mx;
+      // speculative path of a steady-state tile: the scores are the exponents as long as the tile embeds O's reference and
+      // stays below 2^8.  Returns (warp-uniform) whether anything rare is due: reference moved, or a reference to publish.
+      auto tile_fast = [&](const int j) -> bool {
+        mbar_wait(s_full(j & 1), (j >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t s_addr = tmem_base + lane_field + (j & 1) * BKV;
+        const float e = (j & 1) ? e_tile1 : e_tile0;
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+        tmem_ld_32x32b_x32(s_addr, r[0]);
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          tmem_ld_wait();
+          if (ch + 1 < NCH) tmem_ld_32x32b_x32(s_addr + 32 * (ch + 1), r[ch + 1]);
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            m0 = fmax3(m0, __uint_as_float(r[ch][i]), __uint_as_float(r[ch][i + 1]));
+            m1 = fmax3(m1, __uint_as_float(r[ch][i + 2]), __uint_as_float(r[ch][i + 3]));
+            m2 = fmax3(m2, __uint_as_float(r[ch][i + 4]), __uint_as_float(r[ch][i + 5]));
+            m3 = fmax3(m3, __uint_as_float(r[ch][i + 6]), __uint_as_float(r[ch][i + 7]));
+          }
+          uint32_t pk[16];
+          fa_exp32<false, false, 1>(r[ch], pk, 0.f, 0.f, 32 * ch, 0, dummy0, dummy1);
+          tmem_st_32x32b_x16(s_addr + 16 * ch, pk);
+        }
+        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        return __any_sync(0xffffffffu, !(e == m_O && mx <= RESCALE_LOG2) || e_q != m_O);
+      };
+      // first / last tile of the unit (no reference yet / possibly masked columns): all scores first, then their maximum
+      auto tile_plain = [&](const int j) {
         mbar_wait(s_full(j & 1), (j >> 1) & 1u);
         tc_fence_after();
         const uint32_t s_addr = tmem_base + lane_field + (j & 1) * BKV;
         const int n_valid = p.L - (j_lo + j) * BKV;
-        const bool tail = PLAIN && n_valid < BKV;
-        constexpr int NCH = BKV / 32;
-        uint32_t r[NCH][32];
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) tmem_ld_32x32b_x32(s_addr + 32 * ch, r[ch]);
+        tmem_ld_wait();
+        mx = n_valid < BKV ? fa_row_max<NCH, true>(r, n_valid) : fa_row_max<NCH, false>(r, n_valid);
+      };
+      // the rare work of a tile whose scores (r) and row maximum (mx) are in registers: settle the reference, recompute P
+      // with it, rescale O, republish the reference for the tiles whose QK has not been issued yet
+      auto tile_rare = [&](const int j) {
+        const uint32_t s_addr = tmem_base + lane_field + (j & 1) * BKV;
+        const int n_valid = p.L - (j_lo + j) * BKV;
+        const bool tail = n_valid < BKV;
         const float e = (j & 1) ? e_tile1 : e_tile0;
-        float mx;
-        bool slow;
-        if constexpr (PLAIN) {
+        float alpha = 1.f;
+        // keep O's reference unless the row maximum exceeds it by more than 2^8, then move it to the maximum (rounded UP
+        // to fp16 so that it can be embedded exactly)
+        const float abs_max = e + mx;
+        float r_new = m_O;
+        if (!(abs_max - m_O <= RESCALE_LOG2)) r_new = __half2float(__float2half_ru(abs_max));   // also the first tile (m_O = -inf)
+        if (r_new != m_O) {
+          alpha = ex2_approx(m_O - r_new);       // 0 on the first tile
+          m_O = r_new;
+        }
+        const float delta = m_O - e;              // exponent = s' - delta
 #pragma unroll
-          for (int ch = 0; ch < NCH; ++ch) tmem_ld_32x32b_x32(s_addr + 32 * ch, r[ch]);
-          tmem_ld_wait();
-          mx = tail ? fa_row_max<NCH, true>(r, n_valid) : fa_row_max<NCH, false>(r, n_valid);
-          slow = true;
-        } else {
-          // speculative: the scores are the exponents as long as this tile embeds O's reference and stays below 2^8
-          float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-          tmem_ld_32x32b_x32(s_addr, r[0]);
+        for (int ch = 0; ch < NCH; ++ch) {
+          uint32_t pk[16];
+          if (tail) fa_exp32<true, false, 2>(r[ch], pk, 0.f, delta, 32 * ch, n_valid, dummy0, dummy1);
+          else fa_exp32<false, false, 2>(r[ch], pk, 0.f, delta, 32 * ch, n_valid, dummy0, dummy1);
+          tmem_st_32x32b_x16(s_addr + 16 * ch, pk);
+        }
+        if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+          mbar_wait(o_ready((j - 1) & 1), ((j - 1) >> 1) & 1u);
+          tc_fence_after();
 #pragma unroll
-          for (int ch = 0; ch < NCH; ++ch) {
+          for (int cb = 0; cb < C::DV_N; cb += 16) {
+            uint32_t ro[16];
+            tmem_ld_32x32b_x16(tmem_o + lane_field + cb, ro);
             tmem_ld_wait();
-            if (ch + 1 < NCH) tmem_ld_32x32b_x32(s_addr + 32 * (ch + 1), r[ch + 1]);
 #pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              m0 = fmax3(m0, __uint_as_float(r[ch][i]), __uint_as_float(r[ch][i + 1]));
-              m1 = fmax3(m1, __uint_as_float(r[ch][i + 2]), __uint_as_float(r[ch][i + 3]));
-              m2 = fmax3(m2, __uint_as_float(r[ch][i + 4]), __uint_as_float(r[ch][i + 5]));
-              m3 = fmax3(m3, __uint_as_float(r[ch][i + 6]), __uint_as_float(r[ch][i + 7]));
-            }
-            uint32_t pk[16];
-            fa_exp32<false, false, 1>(r[ch], pk, 0.f, 0.f, 32 * ch, n_valid, dummy0, dummy1);
-            tmem_st_32x32b_x16(s_addr + 16 * ch, pk);
-          }
-          mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-          slow = !(e == m_O && mx <= RESCALE_LOG2);
-        }
-        // everything below the speculative path is rare after the first tiles: one warp-uniform branch around it
-        if (PLAIN || __any_sync(0xffffffffu, slow || e_q != m_O)) {
-          float alpha = 1.f;
-          if (PLAIN || __any_sync(0xffffffffu, slow)) {
-            // settle the reference for this tile: keep O's unless the row maximum exceeds it by more than 2^8, then move
-            // it to the maximum (rounded UP to fp16 so that it can be embedded exactly)
-            const float abs_max = e + mx;
-            float r_new = m_O;
-            if (!(abs_max - m_O <= RESCALE_LOG2)) r_new = __half2float(__float2half_ru(abs_max));   // also the first tile (m_O = -inf)
-            if (r_new != m_O) {
-              alpha = ex2_approx(m_O - r_new);       // 0 on the first tile
-              m_O = r_new;
-            }
-            const float delta = m_O - e;              // exponent = s' - delta
-#pragma unroll
-            for (int ch = 0; ch < NCH; ++ch) {
-              uint32_t pk[16];
-              if (tail) fa_exp32<true, false, 2>(r[ch], pk, 0.f, delta, 32 * ch, n_valid, dummy0, dummy1);
-              else fa_exp32<false, false, 2>(r[ch], pk, 0.f, delta, 32 * ch, n_valid, dummy0, dummy1);
-              tmem_st_32x32b_x16(s_addr + 16 * ch, pk);
-            }
-          }
-          if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
-            mbar_wait(o_ready((j - 1) & 1), ((j - 1) >> 1) & 1u);
-            tc_fence_after();
-#pragma unroll
-            for (int cb = 0; cb < C::DV_N; cb += 16) {
-              uint32_t ro[16];
-              tmem_ld_32x32b_x16(tmem_o + lane_field + cb, ro);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
-              tmem_st_32x32b_x16(tmem_o + lane_field + cb, ro);
-            }
-          }
-          // publish O's reference for the tiles whose QK has not been issued yet (j + 2 onwards)
-          if (j + 2 < nkv && __any_sync(0xffffffffu, e_q != m_O)) {
-            // QK of tile j + 1 (issued with the old column) may still be reading this Q tile: wait for its commit
-            mbar_wait(s_full((j + 1) & 1), ((j + 1) >> 1) & 1u);
-            if (e_q != m_O) {
-              const unsigned short neg = __half_as_ushort(__float2half_rn(-m_O));
-              asm volatile("st.shared.u16 [%0], %1;" ::"r"(q_ref_addr), "h"(neg) : "memory");
-              e_q = m_O;
-            }
-            fence_proxy_async_smem();    // generic-proxy store -> visible to the tensor core's (async proxy) operand reads
+            for (int i = 0; i < 16; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
+            tmem_st_32x32b_x16(tmem_o + lane_field + cb, ro);
           }
         }
+        if (j + 2 < nkv && __any_sync(0xffffffffu, e_q != m_O)) {
+          // QK of tile j + 1 (issued with the old column) may still be reading this Q tile: wait for its commit
+          mbar_wait(s_full((j + 1) & 1), ((j + 1) >> 1) & 1u);
+          if (e_q != m_O) {
+            const unsigned short neg = __half_as_ushort(__float2half_rn(-m_O));
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(q_ref_addr), "h"(neg) : "memory");
+            e_q = m_O;
+          }
+          fence_proxy_async_smem();    // generic-proxy store -> visible to the tensor core's (async proxy) operand reads
+        }
+      };
+      auto tile_done = [&](const int j) {
         if (j & 1) e_tile1 = e_q; else e_tile0 = e_q;     // what tile j + 2 will embed
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full(j & 1));
       };
-      tile_step(0, std::true_type{});
-      for (int j = 1; j + 1 < nkv; ++j) tile_step(j, std::false_type{});
-      if (nkv > 1) tile_step(nkv - 1, std::true_type{});
+      // The steady-state tiles run in a loop that holds nothing but the speculative path: a tile with rare work BREAKS out
+      // of it, so that the rare code lies behind the loop instead of being jumped over once per tile (the softmax warps lost
+      // 7 % of their samples to instruction fetch after taken branches, profiles/r02_attention_kernel_study.md section 7).
+      tile_plain(0);
+      tile_rare(0);
+      tile_done(0);
+      for (int j = 1; j + 1 < nkv;) {
+        bool rare = false;
+        for (; j + 1 < nkv; ++j) {
+          rare = tile_fast(j);
+          if (rare) break;
+          tile_done(j);
+        }
+        if (!rare) break;
+        tile_rare(j);
+        tile_done(j);
+        ++j;
+      }
+      if (nkv > 1) {
+        tile_plain(nkv - 1);
+        tile_rare(nkv - 1);
+        tile_done(nkv - 1);
+      }
       m_ref = m_O;      // log2 units already (see the partial-result store below)
     } else {
     // same split as the EMB loop above: first / last tile on the plain path, the steady-state tiles in a loop of their own
