@@ -755,95 +755,119 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
       }
       m_ref = m_O;      // log2 units already (see the partial-result store below)
     } else {
-    // same split as the EMB loop above: first / last tile on the plain path, the steady-state tiles in a loop of their own
-    auto tile_step = [&](const int j, auto plain_c) {
-      constexpr bool PLAIN = decltype(plain_c)::value;
+    // same structure as the EMB loop above: plain first / last tile, steady-state tiles in a loop that a tile with rare
+    // work (reference moved) breaks out of
+    constexpr int NCH = BKV / 32;
+    uint32_t r[NCH][32];   // the row's scores, read from TMEM exactly once
+    float alpha = 1.f, sum0 = 0.f, sum1 = 0.f;
+    // ---- speculative path: the reference max moves only when exceeded by 2^RESCALE_LOG2, which is rare after the first
+    //      tiles.  So the exponentials start chunk by chunk with the CURRENT reference while the row maximum is accumulated
+    //      alongside (independent instruction streams; each TMEM load overlaps the previous chunk's MUFU work).  P stays
+    //      <= 2^8 whenever the speculation holds.  Returns (warp-uniform) whether some row's reference moved.
+    auto tile_fast = [&](const int j) -> bool {
+      mbar_wait(s_full(j & 1), (j >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t s_addr = tmem_base + lane_field + (j & 1) * BKV;
+      alpha = 1.f; sum0 = 0.f; sum1 = 0.f;
+      const float mc0 = m_ref * c;
+      float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+      tmem_ld_32x32b_x32(s_addr, r[0]);
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        tmem_ld_wait();
+        if (ch + 1 < NCH) tmem_ld_32x32b_x32(s_addr + 32 * (ch + 1), r[ch + 1]);
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {   // FMNMX3: two scores per instruction, four independent chains
+          m0 = fmax3(m0, __uint_as_float(r[ch][i]), __uint_as_float(r[ch][i + 1]));
+          m1 = fmax3(m1, __uint_as_float(r[ch][i + 2]), __uint_as_float(r[ch][i + 3]));
+          m2 = fmax3(m2, __uint_as_float(r[ch][i + 4]), __uint_as_float(r[ch][i + 5]));
+          m3 = fmax3(m3, __uint_as_float(r[ch][i + 6]), __uint_as_float(r[ch][i + 7]));
+        }
+        uint32_t pk[16];
+        fa_exp32<false, !ONES>(r[ch], pk, c, mc0, 32 * ch, 0, sum0, sum1);
+        tmem_st_32x32b_x16(s_addr + 16 * ch, pk);
+      }
+      const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      const bool moved = (mx - m_ref) * c > RESCALE_LOG2;
+      if (moved) {
+        alpha = ex2_approx((m_ref - mx) * c);
+        m_ref = mx;
+      }
+      return __any_sync(0xffffffffu, moved);
+    };
+    // ---- plain path (first tile: no reference yet; last tile: masked columns): max first, then the reference
+    auto tile_plain = [&](const int j) {
       mbar_wait(s_full(j & 1), (j >> 1) & 1u);
       tc_fence_after();
       const uint32_t s_addr = tmem_base + lane_field + (j & 1) * BKV;
       const int n_valid = p.L - (j_lo + j) * BKV;  // keys of this tile that exist
-      const bool tail = PLAIN && n_valid < BKV;
-      constexpr int NCH = BKV / 32;
-      uint32_t r[NCH][32];   // the row's scores, read from TMEM exactly once
-      float alpha = 1.f, sum0 = 0.f, sum1 = 0.f;
-      bool redo;
-      if constexpr (PLAIN) {
-        // ---- plain path (first tile: no reference yet; last tile: masked columns): max first, then exponentials
+      alpha = 1.f;
 #pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) tmem_ld_32x32b_x32(s_addr + 32 * ch, r[ch]);
-        tmem_ld_wait();
-        const float mx = tail ? fa_row_max<NCH, true>(r, n_valid) : fa_row_max<NCH, false>(r, n_valid);
-        if ((mx - m_ref) * c > RESCALE_LOG2) {
-          alpha = ex2_approx((m_ref - mx) * c);     // 0 on the first tile (m_ref = -inf)
-          m_ref = mx;
-        }
-        redo = true;                                // "redo" = compute P below with the settled reference
-      } else {
-        // ---- speculative path: the reference max moves only when exceeded by 2^RESCALE_LOG2, which is rare after
-        //      the first tiles.  So the exponentials start chunk by chunk with the CURRENT reference while the
-        //      row maximum is accumulated alongside (independent instruction streams; each TMEM load overlaps the
-        //      previous chunk's MUFU work).  P stays <= 2^8 whenever the speculation holds.
-        const float mc0 = m_ref * c;
-        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-        tmem_ld_32x32b_x32(s_addr, r[0]);
+      for (int ch = 0; ch < NCH; ++ch) tmem_ld_32x32b_x32(s_addr + 32 * ch, r[ch]);
+      tmem_ld_wait();
+      const float mx = n_valid < BKV ? fa_row_max<NCH, true>(r, n_valid) : fa_row_max<NCH, false>(r, n_valid);
+      if ((mx - m_ref) * c > RESCALE_LOG2) {
+        alpha = ex2_approx((m_ref - mx) * c);     // 0 on the first tile (m_ref = -inf)
+        m_ref = mx;
+      }
+    };
+    // ---- P from the kept scores with the settled reference; O rescaled where a reference moved (only after
+    //      P_{j-1} V_{j-1} has retired)
+    auto tile_rare = [&](const int j) {
+      const uint32_t s_addr = tmem_base + lane_field + (j & 1) * BKV;
+      const int n_valid = p.L - (j_lo + j) * BKV;
+      const bool tail = n_valid < BKV;
+      const float mc = m_ref * c;
+      sum0 = 0.f;
+      sum1 = 0.f;
 #pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) {
+      for (int ch = 0; ch < NCH; ++ch) {
+        uint32_t pk[16];
+        if (tail) fa_exp32<true, !ONES>(r[ch], pk, c, mc, 32 * ch, n_valid, sum0, sum1);
+        else fa_exp32<false, !ONES>(r[ch], pk, c, mc, 32 * ch, n_valid, sum0, sum1);
+        tmem_st_32x32b_x16(s_addr + 16 * ch, pk);
+      }
+      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+        mbar_wait(o_ready((j - 1) & 1), ((j - 1) >> 1) & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int cb = 0; cb < C::DV_N; cb += 16) {
+          uint32_t ro[16];
+          tmem_ld_32x32b_x16(tmem_o + lane_field + cb, ro);
           tmem_ld_wait();
-          if (ch + 1 < NCH) tmem_ld_32x32b_x32(s_addr + 32 * (ch + 1), r[ch + 1]);
 #pragma unroll
-          for (int i = 0; i < 32; i += 8) {   // FMNMX3: two scores per instruction, four independent chains
-            m0 = fmax3(m0, __uint_as_float(r[ch][i]), __uint_as_float(r[ch][i + 1]));
-            m1 = fmax3(m1, __uint_as_float(r[ch][i + 2]), __uint_as_float(r[ch][i + 3]));
-            m2 = fmax3(m2, __uint_as_float(r[ch][i + 4]), __uint_as_float(r[ch][i + 5]));
-            m3 = fmax3(m3, __uint_as_float(r[ch][i + 6]), __uint_as_float(r[ch][i + 7]));
-          }
-          uint32_t pk[16];
-          fa_exp32<false, !ONES>(r[ch], pk, c, mc0, 32 * ch, n_valid, sum0, sum1);
-          tmem_st_32x32b_x16(s_addr + 16 * ch, pk);
-        }
-        const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-        const bool moved = (mx - m_ref) * c > RESCALE_LOG2;
-        redo = __any_sync(0xffffffffu, moved);      // warp-uniform; false in the steady state
-        if (moved) {
-          alpha = ex2_approx((m_ref - mx) * c);
-          m_ref = mx;
+          for (int i = 0; i < 16; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
+          tmem_st_32x32b_x16(tmem_o + lane_field + cb, ro);
         }
       }
-      if (redo) {     // one branch around everything rare: recompute P, rescale O
-        const float mc = m_ref * c;
-        sum0 = 0.f;
-        sum1 = 0.f;
-#pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) {
-          uint32_t pk[16];
-          if (tail) fa_exp32<true, !ONES>(r[ch], pk, c, mc, 32 * ch, n_valid, sum0, sum1);
-          else fa_exp32<false, !ONES>(r[ch], pk, c, mc, 32 * ch, n_valid, sum0, sum1);
-          tmem_st_32x32b_x16(s_addr + 16 * ch, pk);
-        }
-        // ---- O rescale: only when a reference max moved, and only after P_{j-1} V_{j-1} has retired
-        if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
-          mbar_wait(o_ready((j - 1) & 1), ((j - 1) >> 1) & 1u);
-          tc_fence_after();
-#pragma unroll
-          for (int cb = 0; cb < C::DV_N; cb += 16) {
-            uint32_t ro[16];
-            tmem_ld_32x32b_x16(tmem_o + lane_field + cb, ro);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
-            tmem_st_32x32b_x16(tmem_o + lane_field + cb, ro);
-          }
-        }
-      }
+    };
+    auto tile_done = [&](const int j) {
       if (!ONES) l_run = l_run * alpha + (sum0 + sum1);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full(j & 1));
     };
-    tile_step(0, std::true_type{});
-    for (int j = 1; j + 1 < nkv; ++j) tile_step(j, std::false_type{});
-    if (nkv > 1) tile_step(nkv - 1, std::true_type{});
+    tile_plain(0);
+    tile_rare(0);
+    tile_done(0);
+    for (int j = 1; j + 1 < nkv;) {
+      bool rare = false;
+      for (; j + 1 < nkv; ++j) {
+        rare = tile_fast(j);
+        if (rare) break;
+        tile_done(j);
+      }
+      if (!rare) break;
+      tile_rare(j);
+      tile_done(j);
+      ++j;
+    }
+    if (nkv > 1) {
+      tile_plain(nkv - 1);
+      tile_rare(nkv - 1);
+      tile_done(nkv - 1);
+    }
     }
     mbar_wait(o_ready((nkv - 1) & 1), ((nkv - 1) >> 1) & 1u);
     tc_fence_after();
