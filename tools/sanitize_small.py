@@ -17,11 +17,15 @@ for (M, N, K) in [(333, 320, 320), (1000, 960, 320), (130, 1920, 640)]:
     y = ops.linear(a, w, b)
     assert torch.isfinite(y).all()
 # attention: one plain shape, one whose last wave is split over key ranges
-for (B, L, C, H) in [(1, 333, 320, 8), (2, 2561, 640, 8)]:
+for (B, L, C, H) in [(1, 333, 320, 8), (2, 2561, 640, 8), (3, 1500, 320, 8), (1, 700, 320, 5)]:
     x = torch.randn((B, L, C), generator=g, device="cuda").half()
     ws = [(torch.randn((C, C), generator=g, device="cuda") / C ** 0.5).half() for _ in range(4)]
     y = ops.attention(x, torch.cat(ws[:3], 0).contiguous(), ws[3], torch.zeros(C, device="cuda").half(), H, (C // H) ** -0.5)
     assert torch.isfinite(y).all()
+if os.environ.get("VTM_SANITIZE_ONLY") == "attention":   # e.g. a second pass with VTM_FA_PAIRS=1 / VTM_FA_GROUPS=1
+    torch.cuda.synchronize()
+    print("sanitize_small (attention only): ok")
+    sys.exit(0)
 # the merge plan (K0, KA with the filtered epilogue, sort, maps, KC, KE), both KA builds
 info = {"size": (16, 16), "args": dict(max_downsample=2, batch_size=2, align_batch=False, merge_global=False,
                                         global_merge_ratio=0.8, local_merge_ratio=0.9, global_rand=0.5, target_stride=4)}

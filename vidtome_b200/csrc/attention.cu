@@ -306,7 +306,7 @@ __device__ __forceinline__ void fa_exp_n(const uint32_t* r, uint32_t* pk, float 
 // each tile's scores embed (QK runs one tile ahead, so a new reference takes effect two tiles later).
 // HALVES == 2 (requires EMB): EIGHT softmax warps per CTA, two per 32-row TMEM quadrant, each taking one half of the tile's
 // keys of the same rows — four softmax warps per scheduler instead of two to cover the fixed-latency dependencies that
-// dominate the stall samples (profiles/r02_attention_kernel_study.md section 7).  With the denominator coming out of the P V MMA
+// dominate the stall samples (profiles/r02_attention_kernel_study.md section 6).  With the denominator coming out of the P V MMA
 // (ONES) and the reference embedded in the scores (EMB) the only thing the two warps of a row share is the decision "the
 // reference moves" — one bar.red.or over the 64 threads per tile in the steady state, plus an exchange of the two half-row
 // maxima through shared memory on the rare tiles where it does.  Each half writes its P into the first half of ITS OWN score
