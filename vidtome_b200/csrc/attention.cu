@@ -25,6 +25,7 @@
 #include <type_traits>
 
 #include "gemm_sm100.cuh"
+#include "gemm_sm100_2cta.cuh"
 
 extern "C" int vtm_linear_f16(const void*, const void*, const void*, int32_t, int32_t, int32_t, void*, int64_t,
                               void*);
@@ -45,6 +46,7 @@ struct HeadSplitEpi {
   static constexpr uint32_t SCRATCH_PER_WARP = gemm::STAGE_STORE_BYTES;
   __half* qkvh;
   int M, C, H, d, L, DP, nb; // M = nb*L rows, C = H*d
+  int dread;                 // columns of a padded row that the flash kernel reads: 16 x (its k-step count) <= DP
   int which0, n_proj;        // this GEMM produces projections which0 .. which0 + n_proj - 1 of (q, k, v); N = n_proj * C
   float qscale;              // q is written as fp16(q * qscale) (1 = plain; softmax scale * log2 e for the embedded reference)
   int kones;                 // also write 1.0 into padding column d of K (embedded reference, flash_attn_kernel EMB)
@@ -80,7 +82,7 @@ struct HeadSplitEpi {
       const bool n_ok = n < n_proj * C && (threadIdx.x & 7) * 8 < ncols - cb;   // BN = 160: 16-column second chunk
       const int which = n / C, c = n - which * C;
       const int head = c / d, e0 = c - head * d;
-      const bool last_group = e0 + 8 == d;                   // then this lane also zeroes the head's padding columns
+      const bool last_group = e0 + 8 == d;                   // then this lane also completes the head's last k-step
       // dst(b, l) = base + (b H L + l) DP: stepped by 4 rows per store (plus (H - 1) L DP when crossing a sample)
       __half* dst = qkvh + which * which_stride + static_cast<long long>(head) * L * DP + e0 +
                     (static_cast<long long>(b0) * H * L + l0) * DP;
@@ -90,13 +92,15 @@ struct HeadSplitEpi {
       gemm::warp_store_rows64(scratch, pk, [&](int, int, const uint4& v) {
         if (bb < nb && n_ok) {
           *reinterpret_cast<uint4*>(dst) = v;
-          if (last_group && d < DP) {
-            // padding columns: zeros — except column d of V, which holds 1.0 so that the P V MMA also produces
-            // the softmax denominator (flash_attn_kernel, ONES)
-            const uint4 z = make_uint4(0, 0, 0, 0);
+          if (last_group && d < dread) {
+            // Columns [d, dread) are read by the flash kernel's last k-step(s) (dread = 16 x its k-step count): zeros —
+            // except column d of V (and of K with `kones`), which holds 1.0 so that the P V MMA also produces the softmax
+            // denominator (flash_attn_kernel, ONES).  The padding beyond dread (up to DP) is never read by an MMA — TMA
+            // copies it into shared memory and nothing else touches it — so it is NOT written: it was 25 % (head_dim 40)
+            // to 37 % (head_dim 80) of this epilogue's stores, and the epilogue is what bounds these GEMMs.
             const bool one = which + which0 == 2 || (kones && which + which0 == 1);
-            *reinterpret_cast<uint4*>(dst + 8) = one ? make_uint4(0x00003C00u, 0, 0, 0) : z;
-            for (int pe = d + 8; pe < DP; pe += 8) *reinterpret_cast<uint4*>(dst + 8 + (pe - d)) = z;
+            *reinterpret_cast<uint4*>(dst + 8) = one ? make_uint4(0x00003C00u, 0, 0, 0) : make_uint4(0, 0, 0, 0);
+            for (int pe = d + 8; pe < dread; pe += 8) *reinterpret_cast<uint4*>(dst + 8 + (pe - d)) = make_uint4(0, 0, 0, 0);
           }
         }
         ll += 4;                                              // next row of this lane: 4 further down
@@ -108,6 +112,15 @@ struct HeadSplitEpi {
   __device__ __forceinline__ void end(int, int, int) {}
 };
 
+// Columns of a head-major padded row that the flash kernels read for head_dim d: 16 x the k-step count of the instantiation
+// launch_fa_any picks (3, 4, 5, 6 or 8).
+inline int fa_columns_read(int d) {
+  const int ks = (d + 15) / 16;
+  return 16 * (ks <= 3 ? 3 : (ks <= 6 ? ks : 8));
+}
+#ifndef VTM_HEAD_PROJ_PAIR_DEFAULT
+#define VTM_HEAD_PROJ_PAIR_DEFAULT 0
+#endif
 // x [nb * L, K] -> projections which0 .. which0 + n_proj - 1 of (q, k, v), head-major padded, at `out`
 // ([n_proj][nb][H][L][DP]); w [n_proj * C, K].
 int launch_head_proj(const void* x, const void* w, __half* out, int nb, int L, int K, int C, int H, int DP, int which0,
@@ -118,12 +131,24 @@ int launch_head_proj(const void* x, const void* w, __half* out, int nb, int L, i
   const int M = nb * L, N = n_proj * C;
   HeadSplitEpi epi;
   epi.qkvh = out; epi.M = M; epi.C = C; epi.H = H; epi.d = C / H; epi.L = L; epi.DP = DP;
+  epi.dread = fa_columns_read(C / H);
   epi.which0 = which0; epi.n_proj = n_proj; epi.qscale = qscale; epi.kones = kones;
   epi.which_stride = static_cast<long long>(nb) * H * L * DP; epi.row0 = 0; epi.scratch = 0; epi.b0 = 0; epi.l0 = 0; epi.nb = nb;
   CUtensorMap ta, tb;
   rc = make_tmap_3d_f16(&ta, x, K, M, 1, K, static_cast<uint64_t>(M) * K, gemm::BK, gemm::BM);
   if (rc) return rc;
   gemm::Work wk;
+  // Wide projections (q, k, v together: N = 3 C) with a short K are bound by the L2 -> SM operand traffic of 128 x 128 tiles
+  // (160 KB per 10.5 MFLOP at K = 320: the ds1 projection ran at 393 TFLOP/s); the CTA-pair mainloop fetches every B byte
+  // once per PAIR of CTAs and uses 256-wide tiles, i.e. half the bytes per FLOP.
+  const int pair_env = gemm::pair_override();
+  if (pair_env != 0 && (pair_env == 1 || VTM_HEAD_PROJ_PAIR_DEFAULT) && N >= 768 && M >= 2048) {
+    rc = make_tmap_3d_f16(&tb, w, K, N, 1, K, static_cast<uint64_t>(N) * K, gemm::BK, 128);
+    if (rc) return rc;
+    gemm::plan_2cta(&wk, M, N, K, 1, sms, 16);
+    wk.n_fastest = 1;
+    return gemm::launch_2cta<HeadSplitEpi>(ta, tb, wk, epi, sms, stream);
+  }
   if (N % 160 == 0 && N % 256 != 0 && N < 960) {     // N = 320 / 640 (q projection of the cross-attention): exact 160-wide tiles
     rc = make_tmap_3d_f16(&tb, w, K, N, 1, K, static_cast<uint64_t>(N) * K, gemm::BK, 160);
     if (rc) return rc;

@@ -10,6 +10,7 @@
 //   * both CTAs' epilogue warps arrive (remotely for the peer) on the leader's accumulator-empty barrier.
 // Work items are decoded per pair; the epilogue policy is the same as in gemm_sm100.cuh.
 #pragma once
+#include <stdlib.h>
 #include "gemm_sm100.cuh"
 
 namespace vtm {
@@ -131,7 +132,9 @@ gemm_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int row_in_tile = quad * 32 + lane;
     uint32_t tile_ctr = 0;
     Epi e = epi;
-    static_assert(Epi::SCRATCH_PER_WARP == 0, "the CTA-pair mainloop has no epilogue staging area");
+    // optional per-warp staging area behind the barriers, as in gemm_sm100.cuh
+    if constexpr (Epi::SCRATCH_PER_WARP > 0)
+      e.set_scratch(bar_base + 256u + static_cast<uint32_t>(warp - 2) * Epi::SCRATCH_PER_WARP);
     for (int w = pair; w < wk.total; w += n_pairs) {
       int m_tile, b, nt0, nt1;
       wk.decode(w, &m_tile, &b, &nt0, &nt1);
@@ -164,17 +167,49 @@ gemm_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
 }
 
+// Work plan for 256-row pair blocks: `wk.m_tiles` counts pair blocks, the n range of a block is split until every pair has
+// about `target_items` items (the pipeline runs straight across item boundaries).
+inline void plan_2cta(Work* wk, int M, int N, int K, int B, int sms, int target_items) {
+  wk->plan(M, N, K, B, Cfg2::BN, sms / 2, target_items, 1);
+  wk->m_tiles = (M + 255) / 256;
+  const long long base = static_cast<long long>(wk->m_tiles) * B;
+  int sp = 1;
+  while (base * sp < static_cast<long long>(target_items) * (sms / 2) && sp * 2 <= wk->n_tiles) sp *= 2;
+  wk->tiles_per_split = (wk->n_tiles + sp - 1) / sp;
+  wk->n_splits = (wk->n_tiles + wk->tiles_per_split - 1) / wk->tiles_per_split;
+  wk->total = static_cast<int>(base * wk->n_splits);
+}
+
 template <class Epi>
 inline int launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const Work& wk, const Epi& epi, int sms,
                        cudaStream_t stream) {
   using C = Cfg2;
-  int rc = cuda_rc(cudaFuncSetAttribute(gemm_kernel_2cta<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(C::SMEM_BYTES)));
+  const size_t smem = C::SMEM_BYTES + static_cast<size_t>(EPI_WARPS) * Epi::SCRATCH_PER_WARP;
+  static_assert(C::SMEM_BYTES + static_cast<size_t>(EPI_WARPS) * Epi::SCRATCH_PER_WARP <= 232448, "shared memory of the pair kernel");
+  // shared-memory opt-in: once per instantiation and device (immutable afterwards)
+  static bool opted[64];
+  int dev = 0;
+  int rc = cuda_rc(cudaGetDevice(&dev));
   if (rc) return rc;
+  if (dev < 0 || dev >= 64 || !opted[dev]) {
+    rc = cuda_rc(cudaFuncSetAttribute(gemm_kernel_2cta<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+    if (rc) return rc;
+    if (dev >= 0 && dev < 64) opted[dev] = true;
+  }
   int pairs = sms / 2;
   if (wk.total < pairs) pairs = wk.total;
-  gemm_kernel_2cta<Epi><<<2 * pairs, THREADS, C::SMEM_BYTES, stream>>>(ta, tb, wk, epi);
+  gemm_kernel_2cta<Epi><<<2 * pairs, THREADS, smem, stream>>>(ta, tb, wk, epi);
   return launch_rc();
+}
+
+// VTM_GEMM_PAIR=0 / 1 overrides the callers' choice between the single-CTA and the CTA-pair mainloop (A/B runs); -1 = unset.
+inline int pair_override() {
+  static const int v = [] {
+    const char* e = getenv("VTM_GEMM_PAIR");
+    return e ? (e[0] == '1' ? 1 : 0) : -1;
+  }();
+  return v;
 }
 
 }  // namespace gemm

@@ -3,6 +3,7 @@
 // reference calls at vidtome/patch.py:157-162).  Uses the shared tcgen05 mainloop; the epilogue converts
 // each thread's accumulator row to fp16 and stores 64-byte runs.
 #include "gemm_sm100.cuh"
+#include "gemm_sm100_2cta.cuh"
 
 namespace vtm {
 namespace {
@@ -157,6 +158,9 @@ struct GegluEpi {
 }  // namespace
 }  // namespace vtm
 
+#ifndef VTM_LINEAR_PAIR_DEFAULT
+#define VTM_LINEAR_PAIR_DEFAULT 0
+#endif
 namespace vtm {
 namespace {
 int linear_impl(const void* a_dev, const void* w_dev, const void* bias_dev, const void* resid_dev, long long ldr,
@@ -187,6 +191,15 @@ int linear_impl(const void* a_dev, const void* w_dev, const void* bias_dev, cons
     return gemm::launch<160, StoreEpi>(ta, tb, wk, epi, sms, stream);
   }
   const bool wide = (N % 256 == 0) || N >= 1024;
+  const int pair_env = gemm::pair_override();
+  if (wide && N % 256 == 0 && M >= 2048 && pair_env != 0 && (pair_env == 1 || VTM_LINEAR_PAIR_DEFAULT)) {
+    // CTA-pair mainloop: every B byte fetched once per pair of CTAs (see launch_head_proj in attention.cu)
+    rc = make_tmap_3d_f16(&tb, w_dev, K, N, 1, K, static_cast<uint64_t>(N) * K, gemm::BK, 128);
+    if (rc) return rc;
+    gemm::plan_2cta(&wk, M, N, K, 1, sms, 16);
+    wk.n_fastest = 1;
+    return gemm::launch_2cta<StoreEpi>(ta, tb, wk, epi, sms, stream);
+  }
   if (wide) {
     rc = make_tmap_3d_f16(&tb, w_dev, K, N, 1, K, static_cast<uint64_t>(N) * K, gemm::BK, 256);
     if (rc) return rc;
@@ -231,9 +244,17 @@ extern "C" int vtm_linear_geglu_f16(const void* a_dev, const void* w_il_dev, con
   CUtensorMap ta, tb;
   rc = make_tmap_3d_f16(&ta, a_dev, K, M, 1, K, static_cast<uint64_t>(M) * K, gemm::BK, gemm::BM);
   if (rc) return rc;
+  gemm::Work wk;
+  const int pair_env = gemm::pair_override();
+  if (N % 256 == 0 && M >= 2048 && pair_env != 0 && (pair_env == 1 || VTM_LINEAR_PAIR_DEFAULT)) {
+    rc = make_tmap_3d_f16(&tb, w_il_dev, K, N, 1, K, static_cast<uint64_t>(N) * K, gemm::BK, 128);
+    if (rc) return rc;
+    gemm::plan_2cta(&wk, M, N, K, 1, sms, 16);
+    wk.n_fastest = 1;
+    return gemm::launch_2cta<GegluEpi>(ta, tb, wk, epi, sms, stream);
+  }
   rc = make_tmap_3d_f16(&tb, w_il_dev, K, N, 1, K, static_cast<uint64_t>(N) * K, gemm::BK, 256);
   if (rc) return rc;
-  gemm::Work wk;
   wk.plan(M, N, K, 1, 256, sms, 16, 1);
   wk.n_fastest = 1;
   return gemm::launch<256, GegluEpi>(ta, tb, wk, epi, sms, stream);

@@ -183,16 +183,7 @@ int sim_argmax_impl(const void* a_dev, const void* b_dev, int32_t B, int32_t Ns,
     rc = make_tmap_3d_f16(&tb2, b_dev, C, Nd, B, C, static_cast<uint64_t>(Nd) * C, gemm::BK, 128);
     if (rc) return rc;
     gemm::Work wk2;
-    wk2.plan(Ns, Nd, C, B, BN, sms / 2, 16, 1);
-    wk2.m_tiles = (Ns + 255) / 256;
-    {  // re-plan the dst split for pair blocks
-      const long long base = static_cast<long long>(wk2.m_tiles) * B;
-      int sp = 1;
-      while (base * sp < 16ll * (sms / 2) && sp * 2 <= wk2.n_tiles) sp *= 2;
-      wk2.tiles_per_split = (wk2.n_tiles + sp - 1) / sp;
-      wk2.n_splits = (wk2.n_tiles + wk2.tiles_per_split - 1) / wk2.tiles_per_split;
-      wk2.total = static_cast<int>(base * wk2.n_splits);
-    }
+    gemm::plan_2cta(&wk2, Ns, Nd, C, B, sms, 16);
     return gemm::launch_2cta<ArgmaxEpi>(ta, tb2, wk2, epi, sms, stream);
   }
   return gemm::launch<BN, ArgmaxEpi>(ta, tb, wk, epi, sms, stream);
