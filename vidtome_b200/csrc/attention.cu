@@ -52,61 +52,104 @@ struct HeadSplitEpi {
   int kones;                 // also write 1.0 into padding column d of K (embedded reference, flash_attn_kernel EMB)
   long long which_stride;    // B*H*L*DP
   int row0;                  // first of the warp's 32 rows
+  int b0, l0;                // (sample, position) of row0 + lane / 8, this lane's first row in the store phase
   uint32_t scratch;
 
   __device__ __forceinline__ void set_scratch(uint32_t a) { scratch = a; }
-  // Integer divisions are ~40 dependent instructions each and this epilogue has only two warps per scheduler to
-  // hide them (they dominated the first version of this kernel): (sample, position) of a row is divided once per
-  // work item and stepped from there, (q/k/v, head, column) once per 64-column chunk.
-  int b0, l0;                // (sample, position) of row row0 + lane / 8, this lane's first row in the store phase
+  // This epilogue, not the MMAs, bounds the projection GEMMs (K = 320 / 640: 0.7 us of MMA per tile): the first version
+  // executed ~940 instructions per warp and 64-column chunk — per-element scale selects, per-store range checks and
+  // sample-wrap loops, two integer divisions per chunk (ncu: 8.6 M warp instructions for 1288 tiles, tensor pipe 26 %).
+  // Everything that is the same for the warp's 32 rows or the chunk's 64 columns is now decided once, warp-uniformly,
+  // and the common case (rows of one sample, all in range; chunk inside one projection) runs without per-store tests.
+  int bw, lw;                // (sample, position) of row0, the first of the warp's 32 rows (warp-uniform)
+  float inv_c, inv_d;        // 1 / C, 1 / d (set by the host) for the exact small-integer divisions below
   __device__ __forceinline__ void begin(int m_tile, int, int row_in_tile) {
     row0 = m_tile * gemm::BM + (row_in_tile & ~31);
-    const int r = row0 + ((row_in_tile & 31) >> 3);
-    b0 = r / L;
-    l0 = r - b0 * L;
+    bw = row0 / L;
+    lw = row0 - bw * L;
+    // this lane's first row in the store phase: row0 + lane / 8
+    b0 = bw;
+    l0 = lw + ((row_in_tile & 31) >> 3);
+    if (l0 >= L) { l0 -= L; ++b0; }
+  }
+  // exact x / y for 0 <= x < 2^22 (x + 0.5 keeps the product away from the integer boundary)
+  static __device__ __forceinline__ int div_small(int x, float inv_y) {
+    return static_cast<int>((static_cast<float>(x) + 0.5f) * inv_y);
   }
   __device__ __forceinline__ void tile(uint32_t taddr, int col0, int ncols) {
+    const int sub = threadIdx.x & 7;
+    const bool rows_plain = lw + 31 < L && bw < nb;      // the warp's 32 rows exist and lie in one sample
 #pragma unroll 1
     for (int cb = 0; cb < ncols; cb += 64) {
       uint32_t r[64];
       tmem_ld_32x32b_x64(taddr + cb, r);
       tmem_ld_wait();
       uint32_t pk[32];
+      const int cfirst = col0 + cb;
+      // q columns are written as fp16(q * qscale): decided per chunk (C is a multiple of 64 for every SD width)
+      if (which0 == 0 && qscale != 1.f && cfirst + 64 <= C) {
+        const uint64_t s2 = f32x2_pack(qscale, qscale);
 #pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        const float sc = (which0 == 0 && col0 + cb + 2 * e < C) ? qscale : 1.f;     // q columns only (C is even)
-        pk[e] = pack_f16x2(__uint_as_float(r[2 * e]) * sc, __uint_as_float(r[2 * e + 1]) * sc);
+        for (int e = 0; e < 32; ++e) {
+          float a, b;
+          f32x2_unpack(f32x2_mul(f32x2_pack(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1])), s2), a, b);
+          pk[e] = pack_f16x2(a, b);
+        }
+      } else if (which0 == 0 && qscale != 1.f && cfirst < C) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const float sc = cfirst + 2 * e < C ? qscale : 1.f;
+          pk[e] = pack_f16x2(__uint_as_float(r[2 * e]) * sc, __uint_as_float(r[2 * e + 1]) * sc);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) pk[e] = pack_f16x2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
       }
       // this lane's 8 columns in the store phase: the same for all of its rows
-      const int n = col0 + cb + (threadIdx.x & 7) * 8;       // groups of 8 columns never straddle a head (d % 8 == 0)
-      const bool n_ok = n < n_proj * C && (threadIdx.x & 7) * 8 < ncols - cb;   // BN = 160: 16-column second chunk
-      const int which = n / C, c = n - which * C;
-      const int head = c / d, e0 = c - head * d;
-      const bool last_group = e0 + 8 == d;                   // then this lane also completes the head's last k-step
+      const int n = cfirst + sub * 8;                        // groups of 8 columns never straddle a head (d % 8 == 0)
+      const bool n_ok = n < n_proj * C && sub * 8 < ncols - cb;   // BN = 160: 16-column second chunk
+      const int which = div_small(n, inv_c), c = n - which * C;
+      const int head = div_small(c, inv_d), e0 = c - head * d;
+      // columns [d, dread) are read by the flash kernel's last k-step(s) (dread = 16 x its k-step count): zeros — except
+      // column d of V (and of K with `kones`), which holds 1.0 so that the P V MMA also produces the softmax denominator
+      // (flash_attn_kernel, ONES).  The padding beyond dread (up to DP) is never read by an MMA — TMA copies it into
+      // shared memory and nothing else touches it — so it is NOT written.
+      const bool pads = e0 + 8 == d && d < dread;
+      const uint4 pad0 = (which + which0 == 2 || (kones && which + which0 == 1)) ? make_uint4(0x00003C00u, 0, 0, 0)
+                                                                                 : make_uint4(0, 0, 0, 0);
       // dst(b, l) = base + (b H L + l) DP: stepped by 4 rows per store (plus (H - 1) L DP when crossing a sample)
       __half* dst = qkvh + which * which_stride + static_cast<long long>(head) * L * DP + e0 +
                     (static_cast<long long>(b0) * H * L + l0) * DP;
-      const long long row_step = 4ll * DP, sample_step = static_cast<long long>(H - 1) * L * DP;
-      int bb = b0, ll = l0;
+      const long long row_step = 4ll * DP;
       // staged through shared memory (gemm::warp_store_rows64): eight lanes write 64 consecutive columns of one row
-      gemm::warp_store_rows64(scratch, pk, [&](int, int, const uint4& v) {
-        if (bb < nb && n_ok) {
-          *reinterpret_cast<uint4*>(dst) = v;
-          if (last_group && d < dread) {
-            // Columns [d, dread) are read by the flash kernel's last k-step(s) (dread = 16 x its k-step count): zeros —
-            // except column d of V (and of K with `kones`), which holds 1.0 so that the P V MMA also produces the softmax
-            // denominator (flash_attn_kernel, ONES).  The padding beyond dread (up to DP) is never read by an MMA — TMA
-            // copies it into shared memory and nothing else touches it — so it is NOT written: it was 25 % (head_dim 40)
-            // to 37 % (head_dim 80) of this epilogue's stores, and the epilogue is what bounds these GEMMs.
-            const bool one = which + which0 == 2 || (kones && which + which0 == 1);
-            *reinterpret_cast<uint4*>(dst + 8) = one ? make_uint4(0x00003C00u, 0, 0, 0) : make_uint4(0, 0, 0, 0);
-            for (int pe = d + 8; pe < dread; pe += 8) *reinterpret_cast<uint4*>(dst + 8 + (pe - d)) = make_uint4(0, 0, 0, 0);
+      if (rows_plain) {
+        if (!n_ok) dst = nullptr;
+        gemm::warp_store_rows64(scratch, pk, [&](int, int, const uint4& v) {
+          if (dst) {
+            *reinterpret_cast<uint4*>(dst) = v;
+            if (pads) {
+              *reinterpret_cast<uint4*>(dst + 8) = pad0;
+              for (int pe = d + 8; pe < dread; pe += 8) *reinterpret_cast<uint4*>(dst + 8 + (pe - d)) = make_uint4(0, 0, 0, 0);
+            }
+            dst += row_step;
           }
-        }
-        ll += 4;                                              // next row of this lane: 4 further down
-        dst += row_step;
-        while (ll >= L) { ll -= L; ++bb; dst += sample_step; }
-      });
+        });
+      } else {
+        const long long sample_step = static_cast<long long>(H - 1) * L * DP;
+        int bb = b0, ll = l0;
+        gemm::warp_store_rows64(scratch, pk, [&](int, int, const uint4& v) {
+          if (bb < nb && n_ok) {
+            *reinterpret_cast<uint4*>(dst) = v;
+            if (pads) {
+              *reinterpret_cast<uint4*>(dst + 8) = pad0;
+              for (int pe = d + 8; pe < dread; pe += 8) *reinterpret_cast<uint4*>(dst + 8 + (pe - d)) = make_uint4(0, 0, 0, 0);
+            }
+          }
+          ll += 4;                                              // next row of this lane: 4 further down
+          dst += row_step;
+          while (ll >= L) { ll -= L; ++bb; dst += sample_step; }
+        });
+      }
     }
   }
   __device__ __forceinline__ void end(int, int, int) {}
@@ -134,6 +177,7 @@ int launch_head_proj(const void* x, const void* w, __half* out, int nb, int L, i
   epi.dread = fa_columns_read(C / H);
   epi.which0 = which0; epi.n_proj = n_proj; epi.qscale = qscale; epi.kones = kones;
   epi.which_stride = static_cast<long long>(nb) * H * L * DP; epi.row0 = 0; epi.scratch = 0; epi.b0 = 0; epi.l0 = 0; epi.nb = nb;
+  epi.bw = 0; epi.lw = 0; epi.inv_c = 1.f / static_cast<float>(C); epi.inv_d = 1.f / static_cast<float>(C / H);
   CUtensorMap ta, tb;
   rc = make_tmap_3d_f16(&ta, x, K, M, 1, K, static_cast<uint64_t>(M) * K, gemm::BK, gemm::BM);
   if (rc) return rc;

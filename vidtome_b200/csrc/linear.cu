@@ -22,7 +22,11 @@ struct StoreEpi {
   __device__ __forceinline__ void begin(int m_tile, int, int row_in_tile) {
     row0 = m_tile * gemm::BM + (row_in_tile & ~31);
   }
+  // As in HeadSplitEpi (attention.cu): with K = 320 .. 1280 this epilogue bounds the GEMM, so whatever is the same for the
+  // warp's 32 rows or the chunk's 64 columns is tested once (warp-uniformly) and the common case — a full chunk inside N, all
+  // rows inside M — runs without per-store range checks (the first version executed ~630 instructions per warp and chunk).
   __device__ __forceinline__ void tile(uint32_t taddr, int col0, int ncols) {
+    const int sub = threadIdx.x & 7;
 #pragma unroll 1
     for (int cb = 0; cb < ncols; cb += 64) {
       uint32_t r[64];
@@ -30,40 +34,71 @@ struct StoreEpi {
       tmem_ld_wait();
       uint32_t pk[32];
       const int c0 = col0 + cb;
+      const bool full = c0 + 64 <= N && ncols - cb >= 64;       // every column of the chunk exists
+      if (bias) {
 #pragma unroll
-      for (int v8 = 0; v8 < 8; ++v8) {         // eight columns at a time: one 16-byte bias load (N % 8 == 0)
-        uint4 bv = make_uint4(0, 0, 0, 0);
-        if (bias && c0 + 8 * v8 < N) bv = __ldg(reinterpret_cast<const uint4*>(bias + c0 + 8 * v8));
-        const __half2* b2 = reinterpret_cast<const __half2*>(&bv);
+        for (int v8 = 0; v8 < 8; ++v8) {         // eight columns at a time: one 16-byte bias load (N % 8 == 0)
+          uint4 bv = make_uint4(0, 0, 0, 0);
+          if (full || c0 + 8 * v8 < N) bv = __ldg(reinterpret_cast<const uint4*>(bias + c0 + 8 * v8));
+          const __half2* b2 = reinterpret_cast<const __half2*>(&bv);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 bf = __half22float2(b2[e]);
-          pk[4 * v8 + e] = pack_f16x2(__uint_as_float(r[8 * v8 + 2 * e]) + bf.x, __uint_as_float(r[8 * v8 + 2 * e + 1]) + bf.y);
+          for (int e = 0; e < 4; ++e) {
+            const float2 bf = __half22float2(b2[e]);
+            float a, b;
+            f32x2_unpack(f32x2_add(f32x2_pack(__uint_as_float(r[8 * v8 + 2 * e]), __uint_as_float(r[8 * v8 + 2 * e + 1])),
+                                   f32x2_pack(bf.x, bf.y)), a, b);
+            pk[4 * v8 + e] = pack_f16x2(a, b);
+          }
         }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) pk[e] = pack_f16x2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
       }
       // store phase: this lane writes columns [c, c + 8) of rows row0 + lane / 8 + 4 i
-      const int c = c0 + (threadIdx.x & 7) * 8;
-      const bool c_ok = c < N && (threadIdx.x & 7) * 8 < ncols - cb;     // BN = 160: the second chunk is 16 columns wide
+      const int c = c0 + sub * 8;
+      const bool c_ok = full || (c < N && sub * 8 < ncols - cb);     // BN = 160: the second chunk is 16 columns wide
       int row = row0 + ((threadIdx.x & 31) >> 3);
       __half* dst = d + static_cast<long long>(row) * ldd + c;
       const __half* rs = resid ? resid + static_cast<long long>(row) * ldr + c : nullptr;
       const long long row_step = 4 * ldd, rrow_step = 4 * ldr;
-      gemm::warp_store_rows64(scratch, pk, [&](int, int, const uint4& v) {
-        if (row < M && c_ok) {
-          uint4 o = v;
-          if (rs) {
+      if (row0 + 31 < M && full) {               // warp-uniform: every row and column of the chunk exists (the staging
+                                                 // inside warp_store_rows64 needs the whole warp on the same path)
+        if (rs) {
+          gemm::warp_store_rows64(scratch, pk, [&](int, int, const uint4& v) {
+            uint4 o = v;
             const uint4 rv = *reinterpret_cast<const uint4*>(rs);
             __half2* a = reinterpret_cast<__half2*>(&o);
             const __half2* b2 = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
             for (int e = 0; e < 4; ++e) a[e] = __hadd2(a[e], b2[e]);
-          }
-          *reinterpret_cast<uint4*>(dst) = o;
+            *reinterpret_cast<uint4*>(dst) = o;
+            dst += row_step;
+            rs += rrow_step;
+          });
+        } else {
+          gemm::warp_store_rows64(scratch, pk, [&](int, int, const uint4& v) {
+            *reinterpret_cast<uint4*>(dst) = v;
+            dst += row_step;
+          });
         }
-        row += 4;
-        dst += row_step;
-        if (rs) rs += rrow_step;
-      });
+      } else {
+        gemm::warp_store_rows64(scratch, pk, [&](int, int, const uint4& v) {
+          if (row < M && c_ok) {
+            uint4 o = v;
+            if (rs) {
+              const uint4 rv = *reinterpret_cast<const uint4*>(rs);
+              __half2* a = reinterpret_cast<__half2*>(&o);
+              const __half2* b2 = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) a[e] = __hadd2(a[e], b2[e]);
+            }
+            *reinterpret_cast<uint4*>(dst) = o;
+          }
+          row += 4;
+          dst += row_step;
+          if (rs) rs += rrow_step;
+        });
+      }
     }
   }
   __device__ __forceinline__ void end(int, int, int) {}
