@@ -161,16 +161,20 @@ struct GegluEpi {
           for (int e = 0; e < 4; ++e) {
             const int i = 8 * v8 + 2 * e;
             const float2 fa = __half22float2(ba2[e]), fg = __half22float2(bg2[e]);
-            // fp16 roundings of the unfused pipeline: projection output, gelu output, product
-            const uint32_t a16 = pack_f16x2(__uint_as_float(r[i]) + fa.x, __uint_as_float(r[i + 1]) + fa.y);
-            const uint32_t g16 = pack_f16x2(__uint_as_float(r[32 + i]) + fg.x, __uint_as_float(r[32 + i + 1]) + fg.y);
-            const float2 af = __half22float2(*reinterpret_cast<const __half2*>(&a16));
+            // fp16 roundings of the unfused pipeline: projection output, gelu output, product.  The adds run on packed
+            // fp32 lanes; the product of the two fp16 values is taken by HMUL2 (the fp32 product of two fp16 numbers is
+            // exact, so one rounding to fp16 either way).
+            float a0, a1, g0, g1;
+            f32x2_unpack(f32x2_add(f32x2_pack(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), f32x2_pack(fa.x, fa.y)), a0, a1);
+            f32x2_unpack(f32x2_add(f32x2_pack(__uint_as_float(r[32 + i]), __uint_as_float(r[32 + i + 1])), f32x2_pack(fg.x, fg.y)), g0, g1);
+            const uint32_t a16 = pack_f16x2(a0, a1);
+            const uint32_t g16 = pack_f16x2(g0, g1);
             const float2 gf = __half22float2(*reinterpret_cast<const __half2*>(&g16));
             float q0, q1;
             gelu_x2(gf.x, gf.y, q0, q1);
             const uint32_t q16 = pack_f16x2(q0, q1);
-            const float2 qf = __half22float2(*reinterpret_cast<const __half2*>(&q16));
-            pk[16 * hlf + 4 * v8 + e] = pack_f16x2(af.x * qf.x, af.y * qf.y);
+            const __half2 prod = __hmul2(*reinterpret_cast<const __half2*>(&a16), *reinterpret_cast<const __half2*>(&q16));
+            pk[16 * hlf + 4 * v8 + e] = *reinterpret_cast<const uint32_t*>(&prod);
           }
         }
       }
@@ -180,11 +184,18 @@ struct GegluEpi {
       __half* dst = d + static_cast<long long>(row) * ldd + c;
       const long long row_step = 4 * ldd;
       const int No = N >> 1;
-      gemm::warp_store_rows64(scratch, pk, [&](int, int, const uint4& v) {
-        if (row < M && c < No) *reinterpret_cast<uint4*>(dst) = v;
-        row += 4;
-        dst += row_step;
-      });
+      if (row0 + 31 < M && oc0 + 64 <= No) {     // warp-uniform: the whole 32 x 64 block exists
+        gemm::warp_store_rows64(scratch, pk, [&](int, int, const uint4& v) {
+          *reinterpret_cast<uint4*>(dst) = v;
+          dst += row_step;
+        });
+      } else {
+        gemm::warp_store_rows64(scratch, pk, [&](int, int, const uint4& v) {
+          if (row < M && c < No) *reinterpret_cast<uint4*>(dst) = v;
+          row += 4;
+          dst += row_step;
+        });
+      }
     }
   }
   __device__ __forceinline__ void end(int, int, int) {}
