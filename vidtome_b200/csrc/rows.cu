@@ -76,7 +76,9 @@ __device__ __forceinline__ __half2 f32x2_to_h2(uint64_t a) {
 }
 // All arithmetic on PACKED fp32 pairs (add / mul / fma .f32x2: the same IEEE operations per lane at half the issue
 // slots, tools/ubench/fma2_pipe.cu).  The row lives in registers as P x 4 pairs.
-template <int G, int P>
+// FULL: the row is exactly G x P vectors wide (C = 320 / 640 / 1280 with G = 8 / 16 / 32, P = 5), so the per-vector range
+// tests — a divergence scaffold of BSSY / BSYNC / BRA around every vector in SASS — are compiled out.
+template <int G, int P, bool FULL = false>
 __device__ __forceinline__ void layer_norm_row(uint4 (&v)[P], int sub, int vecs, int C, float eps,
                                                const float* __restrict__ s_gamma, const float* __restrict__ s_beta) {
   uint64_t f[P][4];
@@ -94,7 +96,7 @@ __device__ __forceinline__ void layer_norm_row(uint4 (&v)[P], int sub, int vecs,
   uint64_t q0 = 0, q1 = 0;
 #pragma unroll
   for (int i = 0; i < P; ++i) {
-    if (sub + G * i < vecs) {
+    if (FULL || sub + G * i < vecs) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) f[i][e] = f32x2_add(f[i][e], nm2);
       q0 = f32x2_fma(f[i][0], f[i][0], q0);
@@ -108,7 +110,7 @@ __device__ __forceinline__ void layer_norm_row(uint4 (&v)[P], int sub, int vecs,
 #pragma unroll
   for (int i = 0; i < P; ++i) {
     const int vi = sub + G * i;
-    if (vi < vecs) {
+    if (FULL || vi < vecs) {
       const ulonglong2 g0 = *reinterpret_cast<const ulonglong2*>(s_gamma + vi * 8), g1 = *reinterpret_cast<const ulonglong2*>(s_gamma + vi * 8 + 4);
       const ulonglong2 b0 = *reinterpret_cast<const ulonglong2*>(s_beta + vi * 8), b1 = *reinterpret_cast<const ulonglong2*>(s_beta + vi * 8 + 4);
       __half2* h = reinterpret_cast<__half2*>(&v[i]);
@@ -124,7 +126,10 @@ __device__ __forceinline__ void layer_norm_row(uint4 (&v)[P], int sub, int vecs,
 // merge.py:84 `metric = metric / metric.norm(dim=-1, keepdim=True)`; merge.py:76-85 split().
 // torch half semantics: norm accumulates in fp32 and is rounded to fp16; the division is carried out
 // in fp32 on the fp16-rounded norm and rounded to fp16.
-template <int G, int P, bool LN>
+// K0 is bound by instruction issue, not by HBM (ncu: 866 warp instructions per two rows of 640 values, issue slots 54 %,
+// DRAM 19 %): FULL (see layer_norm_row) removes the per-vector range tests and the two division variants run as separate
+// loops instead of a test per value pair.
+template <int G, int P, bool LN, bool FULL = false>
 __global__ void __launch_bounds__(ROW_THREADS, LN ? 3 : 4)
 normalize_split_kernel(const __half* __restrict__ x, long long x_bs, const int* __restrict__ rowmap,
                        long long map_bs, Split sp, int B, int C, LnParams ln, __half* __restrict__ a_out,
@@ -164,9 +169,9 @@ normalize_split_kernel(const __half* __restrict__ x, long long x_bs, const int* 
 #pragma unroll
     for (int i = 0; i < P; ++i) {
       v[i] = make_uint4(0, 0, 0, 0);
-      if (live && sub + G * i < vecs) v[i] = ld_nc_16(src + (sub + G * i) * 8);
+      if (live && (FULL || sub + G * i < vecs)) v[i] = ld_nc_16(src + (sub + G * i) * 8);
     }
-    if (LN) layer_norm_row<G, P>(v, sub, vecs, C, ln.eps, s_gamma, s_beta);
+    if (LN) layer_norm_row<G, P, FULL>(v, sub, vecs, C, ln.eps, s_gamma, s_beta);
     uint64_t ss0 = 0, ss1 = 0;
 #pragma unroll
     for (int i = 0; i < P; ++i) {
@@ -186,22 +191,32 @@ normalize_split_kernel(const __half* __restrict__ x, long long x_bs, const int* 
     const bool fast = nrm >= 6.103515625e-05f;
     const float rinv = 1.0f / nrm;
     const uint64_t rinv2 = f32x2_pack(rinv, rinv), nnrm2 = f32x2_pack(-nrm, -nrm);
+    if (fast) {
 #pragma unroll
-    for (int i = 0; i < P; ++i) {
-      if (live && sub + G * i < vecs) {
-        __half2* h = reinterpret_cast<__half2*>(&v[i]);
+      for (int i = 0; i < P; ++i) {
+        if (live && (FULL || sub + G * i < vecs)) {
+          __half2* h = reinterpret_cast<__half2*>(&v[i]);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          if (fast) {
+          for (int e = 0; e < 4; ++e) {
             const uint64_t f2 = h2_to_f32x2(h[e]);
             const uint64_t q0 = f32x2_mul(f2, rinv2);
             h[e] = f32x2_to_h2(f32x2_fma(f32x2_fma(q0, nnrm2, f2), rinv2, q0));
-          } else {
+          }
+          st_16(dst + (sub + G * i) * 8, v[i]);
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int i = 0; i < P; ++i) {
+        if (live && (FULL || sub + G * i < vecs)) {
+          __half2* h = reinterpret_cast<__half2*>(&v[i]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
             const float2 f = __half22float2(h[e]);
             h[e] = __halves2half2(__float2half_rn(f.x / nrm), __float2half_rn(f.y / nrm));
           }
+          st_16(dst + (sub + G * i) * 8, v[i]);
         }
-        st_16(dst + (sub + G * i) * 8, v[i]);
       }
     }
   }
@@ -339,11 +354,14 @@ extern "C" int vtm_normalize_split_ln(const void* x_dev, int64_t x_batch_stride,
   const int vecs = C / 8;
   LnParams ln{static_cast<const __half*>(ln_weight_dev), static_cast<const __half*>(ln_bias_dev), ln_eps};
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
-#define CALL_K0(G, P, LN)                                                                                   \
-  normalize_split_kernel<G, P, LN>                                                                          \
-      <<<grid_for_rows(normalize_split_kernel<G, P, LN>, rows, 32 / G, sms), ROW_THREADS, 0, st>>>(         \
-          static_cast<const __half*>(x_dev), x_batch_stride, rowmap_dev, rowmap_batch_stride, sp, B, C, ln, \
+#define CALL_K0_(G, P, LN, FULL)                                                                                   \
+  normalize_split_kernel<G, P, LN, FULL>                                                                          \
+      <<<grid_for_rows(normalize_split_kernel<G, P, LN, FULL>, rows, 32 / G, sms), ROW_THREADS, 0, st>>>(         \
+          static_cast<const __half*>(x_dev), x_batch_stride, rowmap_dev, rowmap_batch_stride, sp, B, C, ln,       \
           static_cast<__half*>(a_out_dev), static_cast<__half*>(b_out_dev));
+#define CALL_K0(G, P, LN)                                   \
+  if (vecs == (G) * (P)) { CALL_K0_(G, P, LN, true) }       \
+  else { CALL_K0_(G, P, LN, false) }
   if (ln.w) {
 #define CALL(G, P) CALL_K0(G, P, true)
     VTM_DISPATCH_GP_LN(vecs, CALL)
@@ -354,6 +372,7 @@ extern "C" int vtm_normalize_split_ln(const void* x_dev, int64_t x_batch_stride,
 #undef CALL
   }
 #undef CALL_K0
+#undef CALL_K0_
   return launch_rc();
 }
 
