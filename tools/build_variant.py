@@ -1,5 +1,6 @@
 """Build an alternative libvidtome_b200 with extra -D flags into build/variants/<name>/ (tuning sweeps only).
-  python tools/build_variant.py poly7 -DVTM_FA_POLY_NUM=7"""
+  python tools/build_variant.py poly7 -DVTM_FA_POLY_NUM=7
+  python tools/build_variant.py k0pf --src=rows -DVTM_K0_PREFETCH=1      # recompile rows.cu instead of attention.cu"""
 import os
 import subprocess
 import sys
@@ -11,6 +12,8 @@ from vidtome_b200 import _build  # noqa: E402
 
 
 def build(name, defs):
+    srcs_sel = [d.split("=", 1)[1] for d in defs if d.startswith("--src=")] or ["attention"]
+    defs = [d for d in defs if not d.startswith("--src=")]
     out = os.path.join(ROOT, "build", "variants", name)
     os.makedirs(out, exist_ok=True)
     nvcc = _build._nvcc()
@@ -19,7 +22,7 @@ def build(name, defs):
 
     def one(src):
         base = os.path.basename(src)[:-3]
-        affected = base == "attention" or not os.path.exists(os.path.join(_build.OBJDIR, base + ".o"))
+        affected = base in srcs_sel or not os.path.exists(os.path.join(_build.OBJDIR, base + ".o"))
         obj = os.path.join(out, base + ".o") if affected else os.path.join(_build.OBJDIR, base + ".o")
         if affected:
             r = subprocess.run([nvcc, *_build.NVCC_FLAGS, *defs, "-c", src, "-o", obj], capture_output=True, text=True)

@@ -129,8 +129,11 @@ __device__ __forceinline__ void layer_norm_row(uint4 (&v)[P], int sub, int vecs,
 // K0 is bound by instruction issue, not by HBM (ncu: 866 warp instructions per two rows of 640 values, issue slots 54 %,
 // DRAM 19 %): FULL (see layer_norm_row) removes the per-vector range tests and the two division variants run as separate
 // loops instead of a test per value pair.
+#ifndef VTM_K0_PREFETCH
+#define VTM_K0_PREFETCH 0
+#endif
 template <int G, int P, bool LN, bool FULL = false>
-__global__ void __launch_bounds__(ROW_THREADS, LN ? 3 : 4)
+__global__ void __launch_bounds__(ROW_THREADS, VTM_K0_PREFETCH ? (LN ? 2 : 3) : (LN ? 3 : 4))
 normalize_split_kernel(const __half* __restrict__ x, long long x_bs, const int* __restrict__ rowmap,
                        long long map_bs, Split sp, int B, int C, LnParams ln, __half* __restrict__ a_out,
                        __half* __restrict__ b_out) {
@@ -146,31 +149,58 @@ normalize_split_kernel(const __half* __restrict__ x, long long x_bs, const int* 
   const int vecs = C >> 3;
   const long long rows_per_b = static_cast<long long>(sp.Ns) + sp.Nd;
   const long long total = rows_per_b * B;
-  for (long long o0 = warp_id * RPW; o0 < total; o0 += n_warps * RPW) {
+  // where row group o0 comes from and goes to
+  auto locate = [&](long long o0, const __half*& src, __half*& dst) -> bool {
     const long long o = o0 + grp;
-    const bool live = o < total;
-    const __half* src = x;
-    __half* dst = a_out;
-    if (live) {
-      const int b = static_cast<int>(o / rows_per_b);
-      const int q = static_cast<int>(o - b * rows_per_b);
-      int pos;
-      if (q < sp.Ns) {
-        pos = src_pos(sp, q);
-        dst = a_out + (static_cast<long long>(b) * sp.Ns + q) * C;
-      } else {
-        pos = dst_pos(sp, q - sp.Ns);
-        dst = b_out + (static_cast<long long>(b) * sp.Nd + (q - sp.Ns)) * C;
-      }
-      const int row = rowmap ? rowmap[b * map_bs + pos] : pos;
-      src = x + b * x_bs + static_cast<long long>(row) * C;
+    src = x;
+    dst = a_out;
+    if (o >= total) return false;
+    const int b = static_cast<int>(o / rows_per_b);
+    const int q = static_cast<int>(o - b * rows_per_b);
+    int pos;
+    if (q < sp.Ns) {
+      pos = src_pos(sp, q);
+      dst = a_out + (static_cast<long long>(b) * sp.Ns + q) * C;
+    } else {
+      pos = dst_pos(sp, q - sp.Ns);
+      dst = b_out + (static_cast<long long>(b) * sp.Nd + (q - sp.Ns)) * C;
     }
-    uint4 v[P];
+    const int row = rowmap ? rowmap[b * map_bs + pos] : pos;
+    src = x + b * x_bs + static_cast<long long>(row) * C;
+    return true;
+  };
+  auto load_row = [&](uint4 (&w)[P], const __half* src, bool live) {
 #pragma unroll
     for (int i = 0; i < P; ++i) {
-      v[i] = make_uint4(0, 0, 0, 0);
-      if (live && (FULL || sub + G * i < vecs)) v[i] = ld_nc_16(src + (sub + G * i) * 8);
+      w[i] = make_uint4(0, 0, 0, 0);
+      if (live && (FULL || sub + G * i < vecs)) w[i] = ld_nc_16(src + (sub + G * i) * 8);
     }
+  };
+#if VTM_K0_PREFETCH
+  // The rows of the NEXT iteration are requested before the current ones are reduced: one warp iteration is a serial chain
+  // (load -> three shuffle reductions -> division -> store) and with six warps per scheduler the loads were exposed
+  // (profiles/r02_k0_ncu.md).
+  const __half* src_n;
+  __half* dst_n;
+  uint4 v[P], vn[P];
+  long long o0 = warp_id * RPW;
+  bool live_n = locate(o0, src_n, dst_n);
+  load_row(vn, src_n, live_n);
+  for (; o0 < total; o0 += n_warps * RPW) {
+    const bool live = live_n;
+    __half* dst = dst_n;
+#pragma unroll
+    for (int i = 0; i < P; ++i) v[i] = vn[i];
+    live_n = locate(o0 + n_warps * RPW, src_n, dst_n);
+    load_row(vn, src_n, live_n);
+#else
+  for (long long o0 = warp_id * RPW; o0 < total; o0 += n_warps * RPW) {
+    const __half* src;
+    __half* dst;
+    const bool live = locate(o0, src, dst);
+    uint4 v[P];
+    load_row(v, src, live);
+#endif
     if (LN) layer_norm_row<G, P, FULL>(v, sub, vecs, C, ln.eps, s_gamma, s_beta);
     uint64_t ss0 = 0, ss1 = 0;
 #pragma unroll
