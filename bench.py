@@ -232,14 +232,14 @@ def run_reference(args):
     val = 1.0 / step_s
     sample = ("torch fp32 restatement on %d threads: ds1 block call timed %d times (mean %.2f s), ds2 block call timed %d times "
               "(mean %.3f s); step = 5*ds1 + 5*ds2" % (cores, len(t1), m1, len(t2), m2))
-    print(json.dumps({
+    _print_json({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (host)", "data": "synthetic",
         "config": config_dict(max(1, args.gpus), args.workload),
         "cpu_baseline": {"value": val, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    })
 
 
 # ------------------------------------------------------------------------------------------------ GPU helpers
@@ -499,7 +499,7 @@ def run_ours(args):
         config-4 block does not come back (a stuck collective cannot be cancelled, but it must not cost the headline)."""
         if rank == 0 and line and not line.get("_printed"):
             line["_printed"] = True
-            print(json.dumps({k: v for k, v in line.items() if k != "_printed"}), flush=True)
+            _print_json({k: v for k, v in line.items() if k != "_printed"})
 
     if rank == 0:
         pk = peaks()
@@ -601,6 +601,29 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write to fd 1 behind Python's back (NCCL prints its version line
+    there at WARN level), so fd 1 is pointed at stderr for the whole run and the JSON line goes to a private duplicate of
+    the original stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _print_json(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -618,6 +641,7 @@ def main():
                     help="N > 1: skip the secondary BASELINE config-4 block (global-token exchange: all-gather and fused p2p)")
     ap.add_argument("--c4-timeout", type=int, default=240, help="watchdog for the config-4 block, seconds")
     args = ap.parse_args()
+    _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
