@@ -73,6 +73,8 @@ def main():
         runs += [(n + "_no_embed", {"VTM_FA_EMBED": "0"}) for n in names] + [("default_groups", {"VTM_FA_GROUPS": "1"})]
     if "--pairs" in sys.argv:      # eight softmax warps per CTA (flash_attn_kernel HALVES = 2) against four
         runs += [(n + "_pairs1", {"VTM_FA_PAIRS": "1"}) for n in names] + [(n + "_pairs0", {"VTM_FA_PAIRS": "0"}) for n in names]
+    if "--repeat2" in sys.argv:     # interleaved A/B: the whole list twice
+        runs = runs + runs
     for n, extra in runs:
         env = dict(os.environ, VTM_VARIANT=n, **extra)
         base = n.replace("_no_embed", "").replace("_groups", "").replace("_pairs1", "").replace("_pairs0", "")

@@ -404,7 +404,9 @@ __device__ __forceinline__ uint64_t f32x2_sub(uint64_t a, uint64_t b) {
 __device__ __forceinline__ void ex2_poly3_x2(uint64_t x2, float& p0, float& p1) {
   float x0, x1;
   f32x2_unpack(x2, x0, x1);
+#if !defined(VTM_EXP_NO_CLAMP)   // timing experiment only (profiles/r02_attention_kernel_study.md section 6b): unsafe below -126
   x2 = f32x2_pack(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
+#endif
   const uint64_t magic = f32x2_pack(12582912.f, 12582912.f);
   const uint64_t t2 = f32x2_add(x2, magic);
   const uint64_t f2 = f32x2_sub(x2, f32x2_sub(t2, magic));
